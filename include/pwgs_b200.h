@@ -1,0 +1,120 @@
+/* pwgs_b200.h — C ABI of libpwgs_b200.so, the B200 (sm_100a) replacement for the
+ * PhyloWGS Metropolis-Hastings / SSM-likelihood hot path.
+ *
+ * The reference has no FFI for this path: it crosses a PROCESS boundary
+ * (params.py:61 `subprocess.check_call([mh.o, MH_ITR, MH_STD, N_SSM, N_CNV, NNODES,
+ * TREE_HEIGHT, ssm_file, cnv_file, c_tree, c_data_states, c_params, c_mh_ar, NTPS])`,
+ * parsed at mh.cpp:22-61) plus three Python call sites (tssb.py:111,128; evolve.py:188,213).
+ * Each entry point below names the reference interface it replaces.  All citations are
+ * file:line relative to the reference checkout.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative PWGS_E* code; the message is
+ *    available from pwgs_last_error() (thread-local).  Nothing throws or exits.
+ *  - all pointers are HOST pointers to C-contiguous arrays owned by the caller; the
+ *    library copies what it needs during the call and never retains host pointers.
+ *  - int32 / float64 only.  D = n_ssm + n_cnv data; datum index = SSM k -> k,
+ *    CNV k -> n_ssm + k (mh.cpp:256, params.py:71-76).  T = ntps samples, K = tree nodes.
+ *  - a context is bound to one CUDA device and one chain; it is not thread-safe, but
+ *    any number of contexts may coexist in a process (one per chain / per GPU).
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *    PWGS_ECUDA.
+ */
+#ifndef PWGS_B200_H
+#define PWGS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pwgs_ctx pwgs_ctx;
+
+enum {
+    PWGS_OK = 0,
+    PWGS_EINVAL = -1,   /* bad argument (message says which) */
+    PWGS_ECUDA = -2,    /* CUDA runtime error / no device */
+    PWGS_ESTATE = -3,   /* call order (e.g. mh_run before set_tree) */
+    PWGS_ELIMIT = -4    /* problem exceeds a documented limit (K*T shared-memory budget, copy numbers > 32767) */
+};
+
+/* Likelihood conventions. */
+enum {
+    PWGS_SEM_MH = 0,    /* C++: mh.hpp:80-163 — 4 states, 1/4 weights, states substituted as params.py:160-166 */
+    PWGS_SEM_PY = 1     /* Python: data.py:47-126 — states with nv==0 dropped, rest weighted 1/len */
+};
+
+const char *pwgs_last_error(void);
+int pwgs_version(void);
+/* Number of visible CUDA devices (0 and PWGS_ECUDA when there is none). */
+int pwgs_device_count(int *n);
+
+/* Replaces load_ssm_data / load_cnv_data (mh.cpp:208-305) and util2.load_data (util2.py:53-94):
+ * uploads the read counts ONCE per chain instead of re-parsing ssm_data.txt / cnv_data.txt on every
+ * mh.o invocation, and evaluates log_bin_coeff(d,a) (util.cpp:12-14) for every datum x sample on the
+ * device.
+ *   a, d      [D*T] row-major [datum][sample]   (columns a / d of the input files)
+ *   mu_r,mu_v [D]   (CNV rows carry 0.999 / 0.5: mh.cpp:285-286, util2.py:84)
+ *   cnv_ptr   [n_ssm+1] CSR offsets; links of SSM j in cnv-file order (util2.py:86-90)
+ *   cnv_idx   [L] CNV index 0..n_cnv-1 ; cnv_c1/cnv_c2 [L] = tok[1], tok[2] of "sK,c1,c2"
+ * cnv_* may be NULL when n_cnv == 0. */
+int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
+                const int32_t *a, const int32_t *d, const double *mu_r, const double *mu_v,
+                const int32_t *cnv_ptr, const int32_t *cnv_idx, const int32_t *cnv_c1, const int32_t *cnv_c2,
+                pwgs_ctx **out);
+int pwgs_destroy(pwgs_ctx *ctx);
+
+/* Replaces params.write_tree + params.write_data_state (params.py:68-171) and load_tree /
+ * load_data_states (mh.cpp:309-463): hands the current tree to the device and builds the
+ * integer (nr,nv) state coefficients there.
+ *   parent        [K]  parent index, -1 for the single root; any node order
+ *   node_of_datum [D]  node holding each datum
+ *   phi, pi       [K*T] row-major [node][sample]  (node.params, node.pi) */
+int pwgs_set_tree(pwgs_ctx *ctx, int K, const int32_t *parent, const int32_t *node_of_datum,
+                  const double *phi, const double *pi);
+
+/* Replaces `mh.o` (mh.cpp:22-109) as invoked by params.metropolis (params.py:30-65): `iters`
+ * Metropolis-Hastings iterations over (pi, phi) for the tree of the last pwgs_set_tree, in ONE
+ * persistent kernel.  mh_std is rounded to float like mh.hpp:28.  Random stream: Philox4x32-10 keyed
+ * by (seed, stream) — the reference re-seeds MT19937 with GSL's default at every call (mh.cpp:66).
+ *   phi_out, pi_out [K*T]  final node.params / node.pi (update_tree_params, params.py:183-194; full fp64,
+ *                          not the 6 significant digits of write_params mh.cpp:191-204)
+ *   accept_ratio           accepted / iters (c_mh_ar.txt, mh.cpp:104-107)
+ *   llh_out                multi_param_post of the final state (may be NULL) */
+int pwgs_mh_run(pwgs_ctx *ctx, int iters, double mh_std, uint64_t seed, uint64_t stream,
+                double *phi_out, double *pi_out, double *accept_ratio, double *llh_out);
+
+/* Same kernel with the state kept on the device (inputs already resident): launches asynchronously and
+ * records CUDA events around it; pwgs_mh_wait blocks and returns what pwgs_mh_run returns. */
+int pwgs_mh_launch(pwgs_ctx *ctx, int iters, double mh_std, uint64_t seed, uint64_t stream);
+int pwgs_mh_wait(pwgs_ctx *ctx, double *phi_out, double *pi_out, double *accept_ratio, double *llh_out,
+                 float *kernel_ms);
+
+/* Replaces Datum._log_likelihood as called per candidate node by TSSB.resample_assignments
+ * (tssb.py:111,128 -> alleles.py:52 -> data.py:26-62): out[r*K + k] = log-likelihood of datum rows[r]
+ * if it sat in node k of the current tree (all K candidates at once). */
+int pwgs_llh_rows(pwgs_ctx *ctx, int n_rows, const int32_t *rows, int semantics, double *out);
+
+/* semantics MH: multi_param_post of the current state (mh.cpp:147-166).
+ * semantics PY: the data term of TSSB.complete_data_log_likelihood (tssb.py:404-410, alleles.py:55-56). */
+int pwgs_total_llh(pwgs_ctx *ctx, int semantics, double *out);
+
+/* Diagnostics mirroring intermediate files of the reference, used by the parity tests. */
+int pwgs_get_lbc(pwgs_ctx *ctx, double *out /* [D*T] log_bin_coeff(d,a), mh.cpp:234,284 */);
+/* c_data_states.txt (params.py:167-168): *M = number of CNV-affected SSMs; ssm_of_m [M]; coef [M][4][K][2] int32.
+ * Pass NULL arrays to query M only. */
+int pwgs_get_data_states(pwgs_ctx *ctx, int32_t *M, int32_t *ssm_of_m, int32_t *coef);
+
+/* Tuning knobs: "mh_batch" (speculative proposals per grid sync, 1..16), "mh_ctas" (CTAs per chain,
+ * 0 = all SMs), "mh_block" (threads per CTA). */
+int pwgs_set_option(pwgs_ctx *ctx, const char *name, int64_t value);
+int pwgs_get_option(pwgs_ctx *ctx, const char *name, int64_t *value);
+
+/* Measured FP64-pipe issue peak of the device (DFMA chains, thread-instructions/s) — the roofline
+ * denominator for the MH kernel, which is FP64-pipe-bound, not HBM-bound. */
+int pwgs_fp64_peak(int device, double *dfma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

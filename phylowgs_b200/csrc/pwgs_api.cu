@@ -1,0 +1,539 @@
+// pwgs_api.cu — the C ABI of libpwgs_b200.so (include/pwgs_b200.h) over the sm_100a kernels.
+// Host side only owns device memory, validates arguments and launches; there is no CPU compute path:
+// every entry point that produces a likelihood or a sample runs a CUDA kernel or fails with PWGS_ECUDA.
+#include "../../include/pwgs_b200.h"
+#include "pwgs_kernels.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(PWGS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        n = count ? count : 1;
+        return cudaMalloc((void **)&p, n * sizeof(T));
+    }
+    cudaError_t upload(const T *h, size_t count, cudaStream_t s)
+    {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct pwgs_ctx {
+    int device = 0, n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // ---- data set
+    int n_ssm = 0, n_cnv = 0, T = 0, D = 0, Dp = 0, M = 0, L = 0;
+    std::vector<int> ssm_of_m;
+    DevBuf<int> a, d, cnv_ptr, cnv_idx, cnv_c1, cnv_c2;
+    DevBuf<double> mu_r, mu_v, lbc;
+    DevBuf<int> pidx, pa, pd, pnode, cidx, ca, cd;        // permuted work lists (plain first / CNV-affected SSMs)
+    DevBuf<double> pmu_r, pmu_v, cmu_r, clbc;
+    double lbc_plain_sum = 0;
+    // ---- tree
+    bool tree_set = false;
+    int K = 0;
+    DevBuf<int> parent, depth, tin, tout, order, node_of_datum;
+    DevBuf<double> phi, pi;
+    DevBuf<int4> coef;
+    // ---- MH
+    DevBuf<double> partials, phi_out, pi_out, llh_out, scratch;
+    DevBuf<unsigned long long> counter;
+    DevBuf<int> acc_out, rows;
+    DevBuf<MhParams> plist;
+    int opt_batch = 1, opt_ctas = 0, opt_block = 512;
+    bool launched = false;
+    int launched_iters = 0;
+};
+
+static const double kLogTinyMh = log(pow(10, -99));   // mh.hpp:100
+static const double kLogTinyPy = log(1e-99);          // data.py:57
+static const double kLogQuarter = log(0.25);          // mh.hpp:97
+
+static DataView data_view(pwgs_ctx *c)
+{
+    DataView v;
+    v.n_ssm = c->n_ssm; v.n_cnv = c->n_cnv; v.T = c->T;
+    v.a = c->a.p; v.d = c->d.p; v.mu_r = c->mu_r.p; v.mu_v = c->mu_v.p; v.lbc = c->lbc.p;
+    v.cnv_ptr = c->cnv_ptr.p; v.cnv_idx = c->cnv_idx.p; v.cnv_c1 = c->cnv_c1.p; v.cnv_c2 = c->cnv_c2.p;
+    return v;
+}
+static TreeView tree_view(pwgs_ctx *c)
+{
+    TreeView v;
+    v.K = c->K; v.T = c->T;
+    v.parent = c->parent.p; v.depth = c->depth.p; v.tin = c->tin.p; v.tout = c->tout.p;
+    v.phi = c->phi.p; v.pi = c->pi.p; v.node_of_datum = c->node_of_datum.p;
+    return v;
+}
+
+extern "C" {
+
+const char *pwgs_last_error(void) { return g_err.c_str(); }
+int pwgs_version(void) { return 100; }
+
+int pwgs_device_count(int *n)
+{
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (n) *n = (e == cudaSuccess) ? cnt : 0;
+    if (e != cudaSuccess) return fail(PWGS_ECUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return PWGS_OK;
+}
+
+int pwgs_destroy(pwgs_ctx *c)
+{
+    if (!c) return PWGS_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->a.release(); c->d.release(); c->cnv_ptr.release(); c->cnv_idx.release(); c->cnv_c1.release(); c->cnv_c2.release();
+    c->mu_r.release(); c->mu_v.release(); c->lbc.release();
+    c->pidx.release(); c->pa.release(); c->pd.release(); c->pnode.release(); c->cidx.release(); c->ca.release(); c->cd.release();
+    c->pmu_r.release(); c->pmu_v.release(); c->cmu_r.release(); c->clbc.release();
+    c->parent.release(); c->depth.release(); c->tin.release(); c->tout.release(); c->order.release(); c->node_of_datum.release();
+    c->phi.release(); c->pi.release(); c->coef.release();
+    c->partials.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
+    c->counter.release(); c->acc_out.release(); c->rows.release(); c->plist.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return PWGS_OK;
+}
+
+int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
+                const int32_t *a, const int32_t *d, const double *mu_r, const double *mu_v,
+                const int32_t *cnv_ptr, const int32_t *cnv_idx, const int32_t *cnv_c1, const int32_t *cnv_c2,
+                pwgs_ctx **out)
+{
+    if (!out) return fail(PWGS_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n_ssm < 0 || n_cnv < 0 || n_ssm + n_cnv <= 0) return fail(PWGS_EINVAL, "need at least one datum");
+    if (ntps <= 0 || ntps > 65535) return fail(PWGS_EINVAL, "ntps must be in 1..65535");
+    if (!a || !d || !mu_r || !mu_v) return fail(PWGS_EINVAL, "a, d, mu_r, mu_v must not be NULL");
+    const int D = n_ssm + n_cnv, T = ntps;
+    for (size_t i = 0; i < (size_t)D * T; i++)
+        if (a[i] < 0 || d[i] < a[i]) return fail(PWGS_EINVAL, "need 0 <= a <= d for every datum and sample (index " + std::to_string(i) + ")");
+    int L = 0;
+    if (cnv_ptr) {
+        if (cnv_ptr[0] != 0) return fail(PWGS_EINVAL, "cnv_ptr[0] must be 0");
+        for (int j = 0; j < n_ssm; j++) if (cnv_ptr[j + 1] < cnv_ptr[j]) return fail(PWGS_EINVAL, "cnv_ptr must be non-decreasing");
+        L = cnv_ptr[n_ssm];
+        if (L > 0 && (!cnv_idx || !cnv_c1 || !cnv_c2)) return fail(PWGS_EINVAL, "cnv_idx/cnv_c1/cnv_c2 missing");
+        for (int l = 0; l < L; l++) {
+            if (cnv_idx[l] < 0 || cnv_idx[l] >= n_cnv) return fail(PWGS_EINVAL, "cnv_idx out of range");
+            if (cnv_c1[l] < 0 || cnv_c2[l] < 0) return fail(PWGS_EINVAL, "negative copy number");
+            if ((long long)cnv_c1[l] + cnv_c2[l] > 32767) return fail(PWGS_ELIMIT, "copy numbers above 32767 are not supported");
+        }
+    }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PWGS_ECUDA, "no such CUDA device " + std::to_string(device));
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+
+    pwgs_ctx *c = new pwgs_ctx;
+    c->device = device; c->n_sms = prop.multiProcessorCount;
+    c->n_ssm = n_ssm; c->n_cnv = n_cnv; c->T = T; c->D = D; c->L = L;
+#define CREATE_TRY(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            std::string m_ = std::string(#expr) + ": " + cudaGetErrorString(e_);                      \
+            pwgs_destroy(c);                                                                          \
+            return fail(PWGS_ECUDA, m_);                                                              \
+        }                                                                                             \
+    } while (0)
+    CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreate(&c->ev0));
+    CREATE_TRY(cudaEventCreate(&c->ev1));
+    cudaStream_t s = c->stream;
+
+    std::vector<int> zero_ptr(n_ssm + 1, 0), dummy(1, 0);
+    const int *ptr = cnv_ptr ? cnv_ptr : zero_ptr.data();
+    CREATE_TRY(c->a.upload(a, (size_t)D * T, s));
+    CREATE_TRY(c->d.upload(d, (size_t)D * T, s));
+    CREATE_TRY(c->mu_r.upload(mu_r, D, s));
+    CREATE_TRY(c->mu_v.upload(mu_v, D, s));
+    CREATE_TRY(c->cnv_ptr.upload(ptr, n_ssm + 1, s));
+    CREATE_TRY(c->cnv_idx.upload(L ? cnv_idx : dummy.data(), L ? L : 1, s));
+    CREATE_TRY(c->cnv_c1.upload(L ? cnv_c1 : dummy.data(), L ? L : 1, s));
+    CREATE_TRY(c->cnv_c2.upload(L ? cnv_c2 : dummy.data(), L ? L : 1, s));
+    CREATE_TRY(c->lbc.alloc((size_t)D * T));
+    lbc_kernel<<<(D * T + 255) / 256, 256, 0, s>>>(D * T, c->a.p, c->d.p, c->lbc.p);
+    CREATE_TRY(cudaGetLastError());
+
+    // Work lists: "plain" data (mh.hpp:86-89: SSMs outside CNVs and the CNV data themselves) first, then the
+    // CNV-affected SSMs (mh.hpp:90-161).  This split is a property of the inputs, fixed for the chain.
+    std::vector<int> pidx;
+    for (int j = 0; j < D; j++) {
+        bool affected = j < n_ssm && ptr[j + 1] > ptr[j];
+        if (affected) c->ssm_of_m.push_back(j); else pidx.push_back(j);
+    }
+    const int Dp = (int)pidx.size(), M = (int)c->ssm_of_m.size();
+    c->Dp = Dp; c->M = M;
+    std::vector<int> pa((size_t)std::max(Dp, 1) * T), pd((size_t)std::max(Dp, 1) * T), ca((size_t)std::max(M, 1) * T), cd((size_t)std::max(M, 1) * T);
+    std::vector<double> pmr(std::max(Dp, 1)), pmv(std::max(Dp, 1)), cmr(std::max(M, 1));
+    for (int i = 0; i < Dp; i++) {
+        int j = pidx[i];
+        pmr[i] = mu_r[j]; pmv[i] = mu_v[j];
+        for (int tp = 0; tp < T; tp++) { pa[(size_t)tp * Dp + i] = a[(size_t)j * T + tp]; pd[(size_t)tp * Dp + i] = d[(size_t)j * T + tp]; }
+    }
+    for (int m = 0; m < M; m++) {
+        int j = c->ssm_of_m[m];
+        cmr[m] = mu_r[j];
+        for (int tp = 0; tp < T; tp++) { ca[(size_t)tp * M + m] = a[(size_t)j * T + tp]; cd[(size_t)tp * M + m] = d[(size_t)j * T + tp]; }
+    }
+    CREATE_TRY(c->pidx.upload(pidx.data(), Dp, s));
+    CREATE_TRY(c->pa.upload(pa.data(), (size_t)Dp * T, s));
+    CREATE_TRY(c->pd.upload(pd.data(), (size_t)Dp * T, s));
+    CREATE_TRY(c->pmu_r.upload(pmr.data(), Dp, s));
+    CREATE_TRY(c->pmu_v.upload(pmv.data(), Dp, s));
+    CREATE_TRY(c->cidx.upload(c->ssm_of_m.data(), M, s));
+    CREATE_TRY(c->ca.upload(ca.data(), (size_t)M * T, s));
+    CREATE_TRY(c->cd.upload(cd.data(), (size_t)M * T, s));
+    CREATE_TRY(c->cmu_r.upload(cmr.data(), M, s));
+    CREATE_TRY(c->clbc.alloc((size_t)std::max(M, 1) * T));
+    CREATE_TRY(c->pnode.alloc(std::max(Dp, 1)));
+    CREATE_TRY(c->scratch.alloc(4));
+    if (M > 0) {
+        // clbc[tp][m] = lbc of the CNV-affected SSMs, recomputed in place by the same kernel
+        lbc_kernel<<<(M * T + 255) / 256, 256, 0, s>>>(M * T, c->ca.p, c->cd.p, c->clbc.p);
+        CREATE_TRY(cudaGetLastError());
+    }
+    sum_lbc_plain_kernel<<<1, 1024, 0, s>>>(Dp, T, c->pidx.p, c->lbc.p, c->scratch.p);
+    CREATE_TRY(cudaGetLastError());
+    CREATE_TRY(cudaMemcpyAsync(&c->lbc_plain_sum, c->scratch.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CREATE_TRY(cudaStreamSynchronize(s));   // host staging vectors go out of scope below
+    CREATE_TRY(c->counter.alloc(1));
+    CREATE_TRY(c->acc_out.alloc(1));
+    CREATE_TRY(c->llh_out.alloc(1));
+    CREATE_TRY(c->plist.alloc(1));
+#undef CREATE_TRY
+    *out = c;
+    return PWGS_OK;
+}
+
+int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node_of_datum,
+                  const double *phi, const double *pi)
+{
+    if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
+    if (K <= 0 || K > 65535) return fail(PWGS_EINVAL, "K must be in 1..65535");
+    if (!parent || !node_of_datum || !phi || !pi) return fail(PWGS_EINVAL, "NULL array");
+    // ---- validate: exactly one root, in-range parents, no cycles
+    int root = -1;
+    for (int k = 0; k < K; k++) {
+        if (parent[k] < 0) { if (root >= 0) return fail(PWGS_EINVAL, "more than one root"); root = k; }
+        else if (parent[k] >= K || parent[k] == k) return fail(PWGS_EINVAL, "parent index out of range at node " + std::to_string(k));
+    }
+    if (root < 0) return fail(PWGS_EINVAL, "no root (parent == -1) in tree");
+    std::vector<int> depth(K, -1);
+    depth[root] = 0;
+    for (int k = 0; k < K; k++) {
+        int v = k, steps = 0;
+        std::vector<int> path;
+        while (depth[v] < 0) { path.push_back(v); v = parent[v]; if (++steps > K) return fail(PWGS_EINVAL, "cycle in parent array"); }
+        int dd = depth[v];
+        for (int i = (int)path.size() - 1; i >= 0; i--) depth[path[i]] = ++dd;
+    }
+    for (int j = 0; j < c->D; j++)
+        if (node_of_datum[j] < 0 || node_of_datum[j] >= K) return fail(PWGS_EINVAL, "node_of_datum out of range at datum " + std::to_string(j));
+    // ---- Euler tour (children in increasing index) and the children-first accumulation order
+    std::vector<std::vector<int>> kids(K);
+    for (int k = 0; k < K; k++) if (parent[k] >= 0) kids[parent[k]].push_back(k);
+    std::vector<int> tin(K), tout(K), stack{root}, it(K, 0);
+    int clock = 0;
+    tin[root] = clock++;
+    while (!stack.empty()) {
+        int v = stack.back();
+        if (it[v] < (int)kids[v].size()) { int ch = kids[v][it[v]++]; tin[ch] = clock++; stack.push_back(ch); }
+        else { tout[v] = clock++; stack.pop_back(); }
+    }
+    std::vector<int> order(K);
+    for (int k = 0; k < K; k++) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return depth[x] > depth[y]; });
+
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int T = c->T;
+    c->K = K;
+    CUDA_TRY(c->parent.upload(parent, K, s));
+    CUDA_TRY(c->depth.upload(depth.data(), K, s));
+    CUDA_TRY(c->tin.upload(tin.data(), K, s));
+    CUDA_TRY(c->tout.upload(tout.data(), K, s));
+    CUDA_TRY(c->order.upload(order.data(), K, s));
+    CUDA_TRY(c->node_of_datum.upload(node_of_datum, c->D, s));
+    CUDA_TRY(c->phi.upload(phi, (size_t)K * T, s));
+    CUDA_TRY(c->pi.upload(pi, (size_t)K * T, s));
+    CUDA_TRY(c->phi_out.alloc((size_t)K * T));
+    CUDA_TRY(c->pi_out.alloc((size_t)K * T));
+    if (c->Dp > 0) {
+        gather_node_kernel<<<(c->Dp + 255) / 256, 256, 0, s>>>(c->Dp, c->pidx.p, c->node_of_datum.p, c->pnode.p);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(c->coef.alloc((size_t)std::max(c->M, 1) * K));
+    if (c->M > 0) {
+        data_states_kernel<<<(c->M + 127) / 128, 128, 0, s>>>(data_view(c), tree_view(c), c->M, c->cidx.p, c->coef.p);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));   // host arrays (incl. local vectors) may go away after return
+    c->tree_set = true;
+    return PWGS_OK;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------ MH
+static size_t mh_smem_bytes(int K, int T, int B, int block)
+{
+    size_t KT = (size_t)K * T, NW = block / 32;
+    size_t doubles = 4 * KT + T + 4 * (size_t)B * KT + 3 * (size_t)B * T + 2 * (size_t)B + (size_t)B * NW;
+    return doubles * sizeof(double) + 2 * (size_t)K * sizeof(int) + 16;
+}
+
+template <int B>
+static cudaError_t launch_mh(const MhParams *plist, int cpc, int n_chains, int block, size_t smem, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(mh_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    void *args[] = {(void *)&plist, (void *)&cpc};
+    return cudaLaunchCooperativeKernel((void *)mh_kernel<B>, dim3(n_chains * cpc), dim3(block), args, smem, s);
+}
+
+extern "C" {
+
+int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_t stream)
+{
+    if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
+    if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called before pwgs_mh_run");
+    if (iters < 0) return fail(PWGS_EINVAL, "iters must be >= 0");
+    if (!(mh_std > 0)) return fail(PWGS_EINVAL, "mh_std must be > 0");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int B = c->opt_batch;
+    int block = c->opt_block;
+    int cpc = c->opt_ctas > 0 ? std::min(c->opt_ctas, c->n_sms) : c->n_sms;
+    size_t smem = mh_smem_bytes(c->K, c->T, B, block);
+    while (smem > 200 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B, block); }
+    if (smem > 200 * 1024) return fail(PWGS_ELIMIT, "K*T too large for the shared-memory node table");
+    CUDA_TRY(c->partials.alloc((size_t)2 * PWGS_MAX_BATCH * cpc));
+    CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
+
+    MhParams p;
+    p.Dp = c->Dp; p.M = c->M; p.T = c->T; p.K = c->K;
+    p.pa = c->pa.p; p.pd = c->pd.p; p.pmu_r = c->pmu_r.p; p.pmu_v = c->pmu_v.p; p.pnode = c->pnode.p;
+    p.ca = c->ca.p; p.cd = c->cd.p; p.cmu_r = c->cmu_r.p; p.clbc = c->clbc.p; p.coef = c->coef.p;
+    p.parent = c->parent.p; p.order = c->order.p; p.phi0 = c->phi.p; p.pi0 = c->pi.p;
+    p.phi_out = c->phi_out.p; p.pi_out = c->pi_out.p; p.acc_out = c->acc_out.p; p.llh_out = c->llh_out.p;
+    p.iters = iters; p.mh_std = (double)(float)mh_std;   // mh.hpp:28: MH_STD is a float
+    p.seed = seed; p.stream = stream;
+    p.partials = c->partials.p; p.counter = c->counter.p;
+    p.lbc_plain_sum = c->lbc_plain_sum; p.log_tiny = kLogTinyMh; p.log_quarter = kLogQuarter;
+    // pageable source: the runtime stages the bytes before returning, so the stack object is safe
+    CUDA_TRY(cudaMemcpyAsync(c->plist.p, &p, sizeof(p), cudaMemcpyHostToDevice, c->stream));
+
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    cudaError_t e;
+    switch (B) {
+    case 1: e = launch_mh<1>(c->plist.p, cpc, 1, block, smem, c->stream); break;
+    case 2: e = launch_mh<2>(c->plist.p, cpc, 1, block, smem, c->stream); break;
+    case 4: e = launch_mh<4>(c->plist.p, cpc, 1, block, smem, c->stream); break;
+    case 8: e = launch_mh<8>(c->plist.p, cpc, 1, block, smem, c->stream); break;
+    case 16: e = launch_mh<16>(c->plist.p, cpc, 1, block, smem, c->stream); break;
+    default: return fail(PWGS_EINVAL, "mh_batch must be 1, 2, 4, 8 or 16");
+    }
+    if (e != cudaSuccess) return fail(PWGS_ECUDA, std::string("mh_kernel launch: ") + cudaGetErrorString(e));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launched = true;
+    c->launched_iters = iters;
+    return PWGS_OK;
+}
+
+int pwgs_mh_wait(pwgs_ctx *c, double *phi_out, double *pi_out, double *accept_ratio, double *llh_out, float *kernel_ms)
+{
+    if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
+    if (!c->launched) return fail(PWGS_ESTATE, "no MH launch pending");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->launched = false;
+    size_t KT = (size_t)c->K * c->T;
+    int acc = 0;
+    double llh = 0;
+    if (phi_out) CUDA_TRY(cudaMemcpyAsync(phi_out, c->phi_out.p, KT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (pi_out) CUDA_TRY(cudaMemcpyAsync(pi_out, c->pi_out.p, KT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(&acc, c->acc_out.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(&llh, c->llh_out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (accept_ratio) *accept_ratio = c->launched_iters > 0 ? (double)acc / c->launched_iters : 0.0;   // mh.cpp:104-107
+    if (llh_out) *llh_out = llh;
+    if (kernel_ms) CUDA_TRY(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+    return PWGS_OK;
+}
+
+int pwgs_mh_run(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_t stream,
+                double *phi_out, double *pi_out, double *accept_ratio, double *llh_out)
+{
+    int rc = pwgs_mh_launch(c, iters, mh_std, seed, stream);
+    if (rc != PWGS_OK) return rc;
+    return pwgs_mh_wait(c, phi_out, pi_out, accept_ratio, llh_out, nullptr);
+}
+
+// ------------------------------------------------------------------ likelihood grid / totals
+int pwgs_llh_rows(pwgs_ctx *c, int n_rows, const int32_t *rows, int semantics, double *out)
+{
+    if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
+    if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called first");
+    if (n_rows < 0 || (n_rows > 0 && (!rows || !out))) return fail(PWGS_EINVAL, "rows/out NULL");
+    if (semantics != PWGS_SEM_MH && semantics != PWGS_SEM_PY) return fail(PWGS_EINVAL, "unknown semantics");
+    if (n_rows == 0) return PWGS_OK;
+    for (int r = 0; r < n_rows; r++) if (rows[r] < 0 || rows[r] >= c->D) return fail(PWGS_EINVAL, "row index out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    size_t total = (size_t)n_rows * c->K;
+    CUDA_TRY(c->rows.upload(rows, n_rows, c->stream));
+    CUDA_TRY(c->scratch.alloc(total));
+    pair_llh_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(data_view(c), tree_view(c), 0, n_rows, c->rows.p, semantics,
+                                                                            kLogTinyMh, kLogTinyPy, kLogQuarter, c->scratch.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, c->scratch.p, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PWGS_OK;
+}
+
+int pwgs_total_llh(pwgs_ctx *c, int semantics, double *out)
+{
+    if (!c || !out) return fail(PWGS_EINVAL, "NULL argument");
+    if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called first");
+    if (semantics == PWGS_SEM_MH) {
+        // exactly the likelihood path of the MH kernel: zero iterations leave the state alone and report its posterior
+        return pwgs_mh_run(c, 0, 100.0, 0, 0, nullptr, nullptr, nullptr, out);
+    }
+    if (semantics != PWGS_SEM_PY) return fail(PWGS_EINVAL, "unknown semantics");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->scratch.alloc((size_t)c->D + 1));
+    pair_llh_kernel<<<(c->D + 127) / 128, 128, 0, c->stream>>>(data_view(c), tree_view(c), 1, c->D, nullptr, semantics,
+                                                               kLogTinyMh, kLogTinyPy, kLogQuarter, c->scratch.p);
+    CUDA_TRY(cudaGetLastError());
+    sum_kernel<<<1, 1024, 0, c->stream>>>(c->D, c->scratch.p, c->scratch.p + c->D);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, c->scratch.p + c->D, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PWGS_OK;
+}
+
+int pwgs_get_lbc(pwgs_ctx *c, double *out)
+{
+    if (!c || !out) return fail(PWGS_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(out, c->lbc.p, (size_t)c->D * c->T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PWGS_OK;
+}
+
+int pwgs_get_data_states(pwgs_ctx *c, int32_t *M, int32_t *ssm_of_m, int32_t *coef)
+{
+    if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
+    if (M) *M = c->M;
+    if (!ssm_of_m && !coef) return PWGS_OK;
+    if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called first");
+    if (ssm_of_m) for (int m = 0; m < c->M; m++) ssm_of_m[m] = c->ssm_of_m[m];
+    if (coef && c->M > 0) {
+        CUDA_TRY(cudaSetDevice(c->device));
+        std::vector<int4> h((size_t)c->M * c->K);
+        CUDA_TRY(cudaMemcpyAsync(h.data(), c->coef.p, h.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const int K = c->K;
+        for (int m = 0; m < c->M; m++)
+            for (int k = 0; k < K; k++) {
+                int4 v = h[(size_t)k * c->M + m];
+                int w[4] = {v.x, v.y, v.z, v.w};
+                for (int q = 0; q < 4; q++) {          // unpack to the c_data_states layout [m][state][node][nr,nv]
+                    coef[(((size_t)m * 4 + q) * K + k) * 2 + 0] = (short)(w[q] & 0xffff);
+                    coef[(((size_t)m * 4 + q) * K + k) * 2 + 1] = w[q] >> 16;
+                }
+            }
+    }
+    return PWGS_OK;
+}
+
+int pwgs_set_option(pwgs_ctx *c, const char *name, int64_t value)
+{
+    if (!c || !name) return fail(PWGS_EINVAL, "NULL argument");
+    std::string n(name);
+    if (n == "mh_batch") {
+        if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16) return fail(PWGS_EINVAL, "mh_batch must be 1, 2, 4, 8 or 16");
+        c->opt_batch = (int)value;
+    } else if (n == "mh_ctas") {
+        if (value < 0) return fail(PWGS_EINVAL, "mh_ctas must be >= 0");
+        c->opt_ctas = (int)value;
+    } else if (n == "mh_block") {
+        if (value < 64 || value > 512 || value % 32) return fail(PWGS_EINVAL, "mh_block must be a multiple of 32 in 64..512");
+        c->opt_block = (int)value;
+    } else return fail(PWGS_EINVAL, "unknown option " + n);
+    return PWGS_OK;
+}
+
+int pwgs_get_option(pwgs_ctx *c, const char *name, int64_t *value)
+{
+    if (!c || !name || !value) return fail(PWGS_EINVAL, "NULL argument");
+    std::string n(name);
+    if (n == "mh_batch") *value = c->opt_batch;
+    else if (n == "mh_ctas") *value = c->opt_ctas;
+    else if (n == "mh_block") *value = c->opt_block;
+    else if (n == "n_sms") *value = c->n_sms;
+    else if (n == "n_plain") *value = c->Dp;
+    else if (n == "n_cnv_ssm") *value = c->M;
+    else return fail(PWGS_EINVAL, "unknown option " + n);
+    return PWGS_OK;
+}
+
+int pwgs_fp64_peak(int device, double *dfma_per_s)
+{
+    if (!dfma_per_s) return fail(PWGS_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    double *out;
+    CUDA_TRY(cudaMalloc((void **)&out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 20000, block = 512, grid = prop.multiProcessorCount * 4;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        dfma_peak_kernel<<<grid, block>>>(iters, 1.0 + rep, out);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double rate = (double)grid * block * 8.0 * iters / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *dfma_per_s = best;
+    return PWGS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,112 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerances: integer / index work bit-exact; fp64 log-likelihoods within 1e-9 relative (north_star)."""
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) if a.size else 0.0
+
+
+CASES = [
+    dict(n_ssm=300, n_cnv=12, T=1, K=6, seed=11),
+    dict(n_ssm=500, n_cnv=25, T=3, K=12, seed=12),
+    dict(n_ssm=64, n_cnv=6, T=5, K=2, seed=13),
+    dict(n_ssm=1000, n_cnv=0, T=2, K=9, seed=14),
+    dict(n_ssm=700, n_cnv=40, T=1, K=33, seed=15),
+]
+
+
+@pytest.fixture(scope="module", params=range(len(CASES)))
+def case(request, oracle, gpu_lib):
+    data, tree = cases.synthetic_case(oracle, **CASES[request.param])
+    eng = cases.engine_for(gpu_lib, data, tree)
+    yield data, tree, eng
+    eng.close()
+
+
+def test_lbc_matches_log_bin_coeff(case, oracle):
+    data, tree, eng = case
+    assert rel(eng.lbc(), oracle.lbc_table(data)) < 1e-12
+
+
+def test_data_states_bit_exact(case, oracle):
+    data, tree, eng = case
+    ssm_o, coef_o = oracle.data_states(data, tree)
+    ssm_g, coef_g = eng.data_states()
+    assert np.array_equal(ssm_o, ssm_g)
+    assert np.array_equal(coef_o, coef_g)
+
+
+def test_total_llh_mh_semantics(case, oracle, gpu_lib):
+    data, tree, eng = case
+    want = oracle.multi_param_post(data, tree)
+    assert rel(eng.total_llh(gpu_lib.SEM_MH), want) < RTOL
+
+
+def test_total_llh_py_semantics(case, oracle, gpu_lib):
+    data, tree, eng = case
+    want = oracle.total_llh(data, tree, oracle.SEM_PY)
+    assert rel(eng.total_llh(gpu_lib.SEM_PY), want) < RTOL
+
+
+@pytest.mark.parametrize("sem", [0, 1])
+def test_llh_rows(case, oracle, sem):
+    data, tree, eng = case
+    rng = np.random.default_rng(3)
+    rows = np.unique(np.concatenate([rng.integers(0, data.D, size=60), data.cnv_affected[:40], np.arange(data.n_ssm, data.D)]))
+    want = oracle.llh_rows(data, tree, rows, sem)
+    got = eng.llh_rows(rows, sem)
+    assert got.shape == want.shape
+    assert rel(got, want) < RTOL
+
+
+def test_bundled_golden_cases(oracle, gpu_lib):
+    # SURVEY.md section 4, produced by the unmodified reference param_post
+    for with_cnv, golden in ((False, -1872240.7168269958), (True, -1240573.4871084371)):
+        data, tree = cases.bundled(oracle, with_cnv)
+        with cases.engine_for(gpu_lib, data, tree) as eng:
+            assert rel(eng.total_llh(gpu_lib.SEM_MH), golden) < RTOL
+            assert rel(eng.total_llh(gpu_lib.SEM_PY), oracle.total_llh(data, tree, oracle.SEM_PY)) < RTOL
+
+
+@pytest.mark.parametrize("batch", [1, 4, 8])
+@pytest.mark.parametrize("ctas", [1, 3, 0])
+def test_mh_trajectory_matches_oracle(oracle, gpu_lib, batch, ctas):
+    """Same Philox stream => the kernel must walk the oracle's chain: equal accept count, equal final state."""
+    data, tree = cases.synthetic_case(oracle, n_ssm=400, n_cnv=10, T=2, K=7, seed=21)   # random start: many early accepts
+    iters, std, seed, stream = 300, 1000.0, 1234, 7
+    want = oracle.mh_loop(data, tree, iters, std, oracle.RNG_PHILOX, seed, stream)
+    with cases.engine_for(gpu_lib, data, tree) as eng:
+        eng.set_option("mh_batch", batch)
+        eng.set_option("mh_ctas", ctas)
+        got = eng.mh_run(iters, std, seed, stream)
+    assert got["ratio"] * iters == want["accepted"]
+    assert 0 < want["accepted"] < iters
+    assert rel(got["pi"], want["pi"]) < 1e-9
+    assert rel(got["phi"], want["phi"]) < 1e-9
+    assert rel(got["llh"], want["llh"]) < RTOL
+
+
+def test_mh_zero_iterations_is_identity(oracle, gpu_lib):
+    data, tree = cases.bundled(oracle, True)
+    with cases.engine_for(gpu_lib, data, tree) as eng:
+        got = eng.mh_run(0, 100.0)
+    assert np.array_equal(got["pi"], tree.pi) and np.array_equal(got["phi"], tree.phi)
+    assert got["ratio"] == 0.0
+
+
+def test_mh_bundled_example_matches_oracle(oracle, gpu_lib):
+    data, tree = cases.bundled(oracle, True)
+    want = oracle.mh_loop(data, tree, 500, 100.0, oracle.RNG_PHILOX, 99, 3)
+    with cases.engine_for(gpu_lib, data, tree) as eng:
+        got = eng.mh_run(500, 100.0, 99, 3)
+    assert got["ratio"] * 500 == want["accepted"]
+    assert rel(got["pi"], want["pi"]) < 1e-9
+    assert rel(got["llh"], want["llh"]) < RTOL
