@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — MH iterations/s of the PhyloWGS hot path on B200 (metric of BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config3|config4]
+
+One "step" = one `params.metropolis()`-sized pass of the hot path: MH_ITR = 5000 Metropolis-Hastings iterations
+(evolve.py:318 default) over the synthetic WGS tumour of BASELINE.json configs[2] (50k SSMs, 300 CNVs, 8 true
+subclones, T = 1; phylowgs_b200/synth.py, seed 1003) at the fixed truth tree + 2 empty nodes, mh_std = 100
+(SURVEY.md 8d "Bench state").  N > 1 (torchrun): one independent chain per GPU, no data-path collective
+(multievolve.py chains share nothing) => weak scaling; value = iterations of all chains / max-over-ranks time.
+
+  value     device-resident: data, tree and state already in HBM; K back-to-back kernel launches between two
+            CUDA events on the library's stream (an L2 flush is enqueued between launches).
+  e2e       the same K steps through the C-ABI calls a host makes per tree sample (pwgs_set_tree with HOST
+            arrays -> pwgs_mh_run -> HOST phi/pi/ratio), wall-clocked, copies inside the timed region.
+  roofline  the MH kernel is FP64-pipe-bound (its working set, ~2.6 MB, is on-chip for all 5000 iterations), so
+            `bound` is "fp64": achieved = algorithmic FP64-pipe thread-instructions per launch / launch time,
+            peak = DFMA issue rate measured live on the same GPU (pwgs_fp64_peak); the HBM view
+            (algorithmic bytes per iteration x it/s vs MEASURED_PEAKS.json hbm_gbs) is reported beside it.
+  cpu_baseline / --impl reference   the UNMODIFIED reference mh.cpp+util.cpp (oracle/_ref/mh.o, g++ -O3, GSL
+            replaced by oracle/gsl_shim because libgsl is not installable here) on the same inputs written in
+            the reference's text formats; single-threaded => 1 core per chain.
+Nothing here reads /root/reference at run time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MH_ITR = 5000          # evolve.py:318 (--mh-iterations default)
+MH_STD = 100.0         # evolve.py:387
+METRIC = "mh_iterations_per_s"
+UNIT = "it/s"
+
+# FP64-pipe instruction model per likelihood term, counted from this repo's sm_100a SASS (DESIGN.md "Roofline"):
+FP64_PER_PLAIN_TERM = 66.0
+FP64_PER_CNV_TERM_BASE = 400.0
+FP64_PER_CNV_TERM_PER_NODE = 8.0
+
+
+def workload(name):
+    from phylowgs_b200 import synth
+    if name == "config3":
+        return synth.config(3), "synthetic WGS tumour: 50k SSMs, 300 CNVs, 8 true subclones, T=1 (BASELINE.json configs[2])"
+    if name == "config4":
+        return synth.config(4), "synthetic multi-region: 20k SSMs x 5 samples (BASELINE.json configs[3])"
+    raise SystemExit("unknown workload " + name)
+
+
+def algorithmic_work(s, K):
+    """Per MH iteration = ONE proposal-likelihood pass (current-state LLH cached): (bytes, fp64 instructions)."""
+    D, T = s["a"].shape
+    M = int(np.count_nonzero(np.diff(s["cnv_ptr"]) > 0))
+    by = (D - M) * (20 + 8 * T) + M * (12 + 8 * T + 8 * K)
+    fl = FP64_PER_PLAIN_TERM * (D - M) * T + (FP64_PER_CNV_TERM_PER_NODE * K + FP64_PER_CNV_TERM_BASE) * M * T
+    return by, fl, D, M, T
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        res = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return res
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.out.flush()
+        self.out.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.out.read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0]))
+                mx.append(float(t[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.out.close()
+        os.unlink(self.out.name)
+        if sm:
+            res.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return res
+
+
+def write_reference_inputs(s, workdir):
+    """The same state in the reference's own text formats for oracle/_ref/mh.o."""
+    from oracle import oracle as O
+    data = O.Data(s["a"], s["d"], s["mu_r"], s["mu_v"], s["n_ssm"], s["cnv_ptr"], s["cnv_idx"], s["cnv_c1"], s["cnv_c2"])
+    tree = O.Tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
+    f = [os.path.join(workdir, n) for n in ("ssm_data.txt", "cnv_data.txt", "c_tree.txt", "c_data_states.txt")]
+    O.write_ssm_cnv(data, f[0], f[1])
+    O.write_c_tree(tree, f[2], fmt="%.12g")            # py2 str(float) precision, params.py:93
+    ssm_of_m, coef = O.data_states(data, tree)
+    O.write_c_data_states(ssm_of_m, coef, f[3])
+    return f, data, tree
+
+
+def run_mh_o(files, data, tree, iters, workdir, tag="0"):
+    """One invocation of the reference executable (argv of mh.cpp:22-41).  -> (seconds, acceptance ratio)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "mh.o")
+    out = [os.path.join(workdir, "c_params_%s.txt" % tag), os.path.join(workdir, "c_mh_ar_%s.txt" % tag)]
+    cmd = [exe, str(iters), str(MH_STD), str(data.n_ssm), str(data.n_cnv), str(tree.K), "0"] + files + out + [str(data.T)]
+    return cmd, out[1]
+
+
+def time_reference(s, chains, iters_sample):
+    """in-loop MH rate of `chains` concurrent mh.o processes: iters/(t(iters) - t(0)); t(0) = the per-call re-parse."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "mh.o")
+    if not os.path.exists(exe):
+        raise SystemExit("oracle/_ref/mh.o missing: run `python __graft_entry__.py` where /root/reference exists")
+    with tempfile.TemporaryDirectory(prefix="pwgsdataexchange.") as wd:
+        files, data, tree = write_reference_inputs(s, wd)
+
+        def timed(iters):
+            t0 = time.perf_counter()
+            procs = []
+            for c in range(chains):
+                cmd, _ = run_mh_o(files, data, tree, iters, wd, tag=str(c))
+                procs.append(subprocess.Popen(cmd))
+            for p in procs:
+                if p.wait() != 0:
+                    raise SystemExit("reference mh.o failed")
+            return time.perf_counter() - t0
+        t_parse = min(timed(0), timed(0))
+        t_run = timed(iters_sample)
+        ar = float(open(os.path.join(wd, "c_mh_ar_0.txt")).read())
+    loop = max(t_run - t_parse, 1e-9)
+    return dict(rate=chains * iters_sample / loop, t_parse=t_parse, t_run=t_run, accept=ar)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config3")
+    ap.add_argument("--mh-batch", type=int, default=0, help="speculative proposals per grid barrier (0 = library default)")
+    ap.add_argument("--cpu-sample-iters", type=int, default=400, help="MH iterations of the bounded CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = max(args.gpus, world)
+
+    s, wl_desc = workload(args.workload)
+    K = len(s["parent"])
+    by_it, fp_it, D, M, T = algorithmic_work(s, K)
+    config = {"workload": wl_desc, "n_ssm": int(s["n_ssm"]), "n_cnv": int(D - s["n_ssm"]), "n_cnv_affected_ssm": M, "ntps": T,
+              "tree_nodes": K, "mh_iterations_per_step": MH_ITR, "mh_std": MH_STD, "chains": n_gpus, "parallelism": "1 chain per GPU, no collective"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = []
+        acc = None
+        for i in range(args.warmup + args.steps):
+            r = time_reference(s, n_gpus, args.cpu_sample_iters)
+            acc = r["accept"]
+            if i >= args.warmup:
+                steps.append(r)
+        rate = statistics.mean(x["rate"] for x in steps)
+        ms = 1e3 * statistics.mean(x["t_run"] for x in steps)
+        sample = ("%d concurrent oracle/_ref/mh.o (unmodified mh.cpp+util.cpp, g++ -O3, GSL shim), MH_ITR=%d per step on the %s inputs; "
+                  "rate = MH_ITR/(t(MH_ITR)-t(0)), t(0)=%.2fs text re-parse per call excluded" % (n_gpus, args.cpu_sample_iters, args.workload, steps[-1]["t_parse"]))
+        line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "accept_ratio": acc,
+                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": n_gpus, "kind": "reference", "sample": sample},
+                "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    import phylowgs_b200 as P
+    if not torch.cuda.is_available() or P.device_count() == 0:
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from phylowgs_b200 import synth
+    eng = P.Engine(device=local_rank, **synth.data_kwargs(s))
+    eng.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
+    if args.mh_batch:
+        eng.set_option("mh_batch", args.mh_batch)
+    ext = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    seed = 20261019
+
+    for w in range(args.warmup):
+        eng.mh_launch(MH_ITR, MH_STD, seed, 1000 * rank + w)
+        eng.mh_wait(fetch=False)
+    fp64_peak = P.fp64_peak(local_rank)                                 # DFMA thread-instr/s, measured on this GPU now
+
+    # ---- value: device-resident, CUDA events on the library's stream
+    launches0 = eng.get_option("launches")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, ratios = [], []
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    with torch.cuda.stream(ext):
+        e0.record(ext)
+        for k in range(args.steps):
+            flush.zero_()                                               # L2 flush between timed steps (inside the bracket)
+            eng.mh_launch(MH_ITR, MH_STD, seed, 1000 * rank + 100 + k)
+            r = eng.mh_wait(fetch=False)
+            kernel_ms.append(r["kernel_ms"])
+            ratios.append(r["ratio"])
+        e1.record(ext)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.get_option("launches") - launches0
+    value = n_gpus * args.steps * MH_ITR / (total_ms * 1e-3)
+    kms = statistics.mean(kernel_ms)
+
+    # ---- e2e: host arrays in, host arrays out, through the C-ABI calls made once per tree sample
+    h2d = s["parent"].nbytes + s["node_of_datum"].nbytes + s["phi"].nbytes + s["pi"].nbytes
+    d2h = s["phi"].nbytes + s["pi"].nbytes + 8 + 8
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        eng.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
+        eng.mh_run(MH_ITR, MH_STD, seed, 1000 * rank + 200 + k)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = n_gpus * args.steps * MH_ITR / e2e_s
+
+    if rank != 0:
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (mh_kernel), per launch
+    its_kernel = MH_ITR / (kms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {"bound": "fp64", "achieved": fp_it * its_kernel / 1e9, "peak": fp64_peak / 1e9, "unit": "G FP64-instr/s",
+                "frac": fp_it * its_kernel / fp64_peak, "traffic": None,
+                "peak_source": "pwgs_fp64_peak: DFMA chains measured live on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
+                "algorithmic_fp64_instr_per_iteration": fp_it, "kernel_ms_per_launch": kms,
+                "hbm": {"achieved": by_it * its_kernel / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": by_it * its_kernel / 1e9 / hbm_peak,
+                        "algorithmic_bytes_per_iteration": by_it,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        r = time_reference(s, 1, args.cpu_sample_iters)
+        cpu_baseline = {"value": r["rate"], "unit": UNIT, "cores": 1, "kind": "reference",
+                        "sample": "oracle/_ref/mh.o (unmodified mh.cpp+util.cpp, g++ -O3, GSL shim) MH_ITR=%d on the same %s inputs: %.2fs total, "
+                                  "%.2fs of it the per-call text re-parse (excluded from the rate); accept=%.4f; host has %d cores"
+                                  % (args.cpu_sample_iters, args.workload, r["t_run"], r["t_parse"], r["accept"], os.cpu_count())}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(config, l2="256 MiB L2 flush enqueued between timed steps; working set is on-chip by design",
+                                                 mh_batch=eng.get_option("mh_batch")),
+            "accept_ratio": statistics.mean(ratios), "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -110,6 +110,11 @@ int pwgs_get_data_states(pwgs_ctx *ctx, int32_t *M, int32_t *ssm_of_m, int32_t *
 int pwgs_set_option(pwgs_ctx *ctx, const char *name, int64_t value);
 int pwgs_get_option(pwgs_ctx *ctx, const char *name, int64_t *value);
 
+/* The context's cudaStream_t (as void*), so a caller can order its own device work / CUDA events against the
+ * library's launches (bench.py times with events on this stream).  Read-only "launches" option = number of this
+ * library's kernels launched for the context so far. */
+int pwgs_get_stream(pwgs_ctx *ctx, void **stream);
+
 /* Measured FP64-pipe issue peak of the device (DFMA chains, thread-instructions/s) — the roofline
  * denominator for the MH kernel, which is FP64-pipe-bound, not HBM-bound. */
 int pwgs_fp64_peak(int device, double *dfma_per_s);

@@ -328,7 +328,9 @@ def ref_available():
 def ref_lib():
     global _ref
     if _ref is None:
-        R = C.CDLL(os.path.join(HERE, "_ref", "libpwgs_ref.so"))
+        # RTLD_DEEPBIND: the reference .so carries its own (static) libstdc++ and GSL-shim symbols; without it they
+        # get interposed by same-named symbols already in the Python process and the reference mh_loop crashes.
+        R = C.CDLL(os.path.join(HERE, "_ref", "libpwgs_ref.so"), mode=os.RTLD_NOW | os.RTLD_DEEPBIND)
         R.ref_load.restype = C.c_void_p
         R.ref_load.argtypes = [C.c_char_p] * 4 + [C.c_int, C.c_double] + [C.c_int] * 4
         R.ref_free.argtypes = [C.c_void_p]

@@ -31,6 +31,7 @@ SIGNATURES = {
     "pwgs_get_data_states": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p]),
     "pwgs_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "pwgs_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "pwgs_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "pwgs_fp64_peak": (C.c_int, [C.c_int, _f64p]),
 }
 

@@ -67,6 +67,7 @@ struct pwgs_ctx {
     int opt_batch = 1, opt_ctas = 0, opt_block = 512;
     bool launched = false;
     int launched_iters = 0;
+    long long n_launches = 0;                             // kernels of this library launched on behalf of the context
 };
 
 static const double kLogTinyMh = log(pow(10, -99));   // mh.hpp:100
@@ -185,6 +186,7 @@ int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
     CREATE_TRY(c->cnv_c2.upload(L ? cnv_c2 : dummy.data(), L ? L : 1, s));
     CREATE_TRY(c->lbc.alloc((size_t)D * T));
     lbc_kernel<<<(D * T + 255) / 256, 256, 0, s>>>(D * T, c->a.p, c->d.p, c->lbc.p);
+    c->n_launches++;
     CREATE_TRY(cudaGetLastError());
 
     // Work lists: "plain" data (mh.hpp:86-89: SSMs outside CNVs and the CNV data themselves) first, then the
@@ -223,9 +225,11 @@ int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
     if (M > 0) {
         // clbc[tp][m] = lbc of the CNV-affected SSMs, recomputed in place by the same kernel
         lbc_kernel<<<(M * T + 255) / 256, 256, 0, s>>>(M * T, c->ca.p, c->cd.p, c->clbc.p);
+        c->n_launches++;
         CREATE_TRY(cudaGetLastError());
     }
     sum_lbc_plain_kernel<<<1, 1024, 0, s>>>(Dp, T, c->pidx.p, c->lbc.p, c->scratch.p);
+    c->n_launches++;
     CREATE_TRY(cudaGetLastError());
     CREATE_TRY(cudaMemcpyAsync(&c->lbc_plain_sum, c->scratch.p, sizeof(double), cudaMemcpyDeviceToHost, s));
     CREATE_TRY(cudaStreamSynchronize(s));   // host staging vectors go out of scope below
@@ -293,11 +297,13 @@ int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node
     CUDA_TRY(c->pi_out.alloc((size_t)K * T));
     if (c->Dp > 0) {
         gather_node_kernel<<<(c->Dp + 255) / 256, 256, 0, s>>>(c->Dp, c->pidx.p, c->node_of_datum.p, c->pnode.p);
+        c->n_launches++;
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(c->coef.alloc((size_t)std::max(c->M, 1) * K));
     if (c->M > 0) {
         data_states_kernel<<<(c->M + 127) / 128, 128, 0, s>>>(data_view(c), tree_view(c), c->M, c->cidx.p, c->coef.p);
+        c->n_launches++;
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaStreamSynchronize(s));   // host arrays (incl. local vectors) may go away after return
@@ -367,6 +373,7 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     }
     if (e != cudaSuccess) return fail(PWGS_ECUDA, std::string("mh_kernel launch: ") + cudaGetErrorString(e));
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->n_launches++;
     c->launched = true;
     c->launched_iters = iters;
     return PWGS_OK;
@@ -416,6 +423,7 @@ int pwgs_llh_rows(pwgs_ctx *c, int n_rows, const int32_t *rows, int semantics, d
     pair_llh_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(data_view(c), tree_view(c), 0, n_rows, c->rows.p, semantics,
                                                                             kLogTinyMh, kLogTinyPy, kLogQuarter, c->scratch.p);
     CUDA_TRY(cudaGetLastError());
+    c->n_launches++;
     CUDA_TRY(cudaMemcpyAsync(out, c->scratch.p, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PWGS_OK;
@@ -437,6 +445,7 @@ int pwgs_total_llh(pwgs_ctx *c, int semantics, double *out)
     CUDA_TRY(cudaGetLastError());
     sum_kernel<<<1, 1024, 0, c->stream>>>(c->D, c->scratch.p, c->scratch.p + c->D);
     CUDA_TRY(cudaGetLastError());
+    c->n_launches += 2;
     CUDA_TRY(cudaMemcpyAsync(out, c->scratch.p + c->D, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PWGS_OK;
@@ -504,7 +513,15 @@ int pwgs_get_option(pwgs_ctx *c, const char *name, int64_t *value)
     else if (n == "n_sms") *value = c->n_sms;
     else if (n == "n_plain") *value = c->Dp;
     else if (n == "n_cnv_ssm") *value = c->M;
+    else if (n == "launches") *value = c->n_launches;
     else return fail(PWGS_EINVAL, "unknown option " + n);
+    return PWGS_OK;
+}
+
+int pwgs_get_stream(pwgs_ctx *c, void **stream)
+{
+    if (!c || !stream) return fail(PWGS_EINVAL, "NULL argument");
+    *stream = (void *)c->stream;
     return PWGS_OK;
 }
 

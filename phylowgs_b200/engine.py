@@ -105,6 +105,12 @@ class Engine:
         check(_lib.load().pwgs_get_data_states(self._h, C.byref(M), p_i32(ssm), p_i32(coef)))
         return ssm[:M.value], coef[:M.value]
 
+    def stream_handle(self):
+        """cudaStream_t of this context as an int (for torch.cuda.ExternalStream in bench.py)."""
+        h = C.c_void_p()
+        check(_lib.load().pwgs_get_stream(self._h, C.byref(h)))
+        return h.value or 0
+
     def set_option(self, name, value):
         check(_lib.load().pwgs_set_option(self._h, name.encode(), int(value)))
 
