@@ -293,7 +293,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-double orc_u01_from_u64(uint64_t x) { return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+double orc_u01_from_u64(uint64_t x) { return ((double)(x >> 12) + 0.5) * (1.0 / 4503599627370496.0); }
 
 /* Stream layout (DESIGN.md "Random streams"): key = {seed_lo, seed_hi ^ stream_hi};
  * ctr = {iteration, (tp<<16)|node, (purpose<<24)|index, stream_lo}. */

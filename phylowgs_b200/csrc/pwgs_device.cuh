@@ -118,7 +118,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 __device__ __forceinline__ double u01_from_u64(uint64_t x)
 {
-    return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    return ((double)(x >> 12) + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 // Stream layout (DESIGN.md "Random streams"):

@@ -72,3 +72,31 @@ def engine_for(P, data, tree=None, device=0):
     if tree is not None:
         e.set_tree(tree.parent, tree.node_of_datum, tree.phi, tree.pi)
     return e
+
+
+# Seeded synthetic cases whose reference outputs are frozen in tests/golden/ref_vectors.json (make_golden.py).
+GOLDEN_SYNTH = [
+    dict(n_ssm=300, n_cnv=12, T=1, K=6, seed=11),
+    dict(n_ssm=500, n_cnv=25, T=3, K=12, seed=12),
+    dict(n_ssm=64, n_cnv=6, T=5, K=2, seed=13),
+    dict(n_ssm=1000, n_cnv=0, T=2, K=9, seed=14),
+    dict(n_ssm=700, n_cnv=40, T=1, K=33, seed=15),
+]
+
+
+def children_first(tree):
+    """Relabel nodes k -> K-1-k.  For trees with parent[k] < k (all generators here) index order then lists children before
+    parents, which is the file order mh.cpp:134-141 needs; the reference then visits nodes in plain index order and its
+    sequential RNG draws line up with the oracle's."""
+    from oracle import oracle as O
+    K = tree.K
+    assert all(tree.parent[k] < k for k in range(K))
+    perm = K - 1 - np.arange(K)
+    parent = np.full(K, -1, dtype=np.int32)
+    for k in range(K):
+        parent[perm[k]] = perm[tree.parent[k]] if tree.parent[k] >= 0 else -1
+    phi = np.zeros_like(tree.phi)
+    pi = np.zeros_like(tree.pi)
+    phi[perm] = tree.phi
+    pi[perm] = tree.pi
+    return O.Tree(parent, perm[tree.node_of_datum].astype(np.int32), phi, pi)
