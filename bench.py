@@ -67,49 +67,58 @@ def algorithmic_work(s, K):
 
 
 class ClockSampler:
-    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML from a host thread DURING the timed region (the recipe's clocks line;
+    NVML instead of spawning nvidia-smi so that starting the sampler does not itself disturb the timed kernels)."""
 
-    def __init__(self, index):
-        self.proc = None
-        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, index, period_s=0.15):
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self._sample()                      # first query outside the timed region (NVML warm-up)
+            self.samples.clear()
+        except Exception:
+            self.N = None
+            return
+        self.period = period_s
+
+    def _sample(self):
+        N = self.N
+        self.samples.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+        r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+                          ("hw_power_brake_slowdown", 0x80)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def start(self):
+        import threading
+        if self.N is None:
+            return
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self._sample()
+                except Exception:
+                    break
+                self._stop.wait(self.period)
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        res = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return res
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.out.flush()
-        self.out.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.out.read().splitlines():
-            t = [x.strip() for x in line.split(",")]
-            if len(t) < 7:
-                continue
-            try:
-                sm.append(float(t[0]))
-                mx.append(float(t[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, t[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        self.out.close()
-        os.unlink(self.out.name)
-        if sm:
-            res.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
-        return res
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+        sm = self.samples
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def write_reference_inputs(s, workdir):
@@ -125,15 +134,15 @@ def write_reference_inputs(s, workdir):
     return f, data, tree
 
 
-def run_mh_o(files, data, tree, iters, workdir, tag="0"):
+def run_mh_o(files, data, tree, iters, workdir, tag="0", mh_std=MH_STD):
     """One invocation of the reference executable (argv of mh.cpp:22-41).  -> (seconds, acceptance ratio)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "mh.o")
     out = [os.path.join(workdir, "c_params_%s.txt" % tag), os.path.join(workdir, "c_mh_ar_%s.txt" % tag)]
-    cmd = [exe, str(iters), str(MH_STD), str(data.n_ssm), str(data.n_cnv), str(tree.K), "0"] + files + out + [str(data.T)]
+    cmd = [exe, str(iters), str(mh_std), str(data.n_ssm), str(data.n_cnv), str(tree.K), "0"] + files + out + [str(data.T)]
     return cmd, out[1]
 
 
-def time_reference(s, chains, iters_sample):
+def time_reference(s, chains, iters_sample, mh_std=MH_STD):
     """in-loop MH rate of `chains` concurrent mh.o processes: iters/(t(iters) - t(0)); t(0) = the per-call re-parse."""
     exe = os.path.join(ROOT, "oracle", "_ref", "mh.o")
     if not os.path.exists(exe):
@@ -145,7 +154,7 @@ def time_reference(s, chains, iters_sample):
             t0 = time.perf_counter()
             procs = []
             for c in range(chains):
-                cmd, _ = run_mh_o(files, data, tree, iters, wd, tag=str(c))
+                cmd, _ = run_mh_o(files, data, tree, iters, wd, tag=str(c), mh_std=mh_std)
                 procs.append(subprocess.Popen(cmd))
             for p in procs:
                 if p.wait() != 0:
@@ -161,14 +170,17 @@ def time_reference(s, chains, iters_sample):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config3")
     ap.add_argument("--mh-batch", type=int, default=0, help="speculative proposals per grid barrier (0 = library default)")
     ap.add_argument("--cpu-sample-iters", type=int, default=400, help="MH iterations of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mh-std", type=float, default=MH_STD, help="proposal concentration (evolve.py adapts it between 100 and 10000)")
+    ap.add_argument("--profile-phases", action="store_true", help="print the MH kernel's per-phase cycle counters (CTA 0) to stderr")
     args = ap.parse_args()
+    mh_std = args.mh_std
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,7 +190,7 @@ def main():
     K = len(s["parent"])
     by_it, fp_it, D, M, T = algorithmic_work(s, K)
     config = {"workload": wl_desc, "n_ssm": int(s["n_ssm"]), "n_cnv": int(D - s["n_ssm"]), "n_cnv_affected_ssm": M, "ntps": T,
-              "tree_nodes": K, "mh_iterations_per_step": MH_ITR, "mh_std": MH_STD, "chains": n_gpus, "parallelism": "1 chain per GPU, no collective"}
+              "tree_nodes": K, "mh_iterations_per_step": MH_ITR, "mh_std": mh_std, "chains": n_gpus, "parallelism": "1 chain per GPU, no collective"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -187,7 +199,7 @@ def main():
         steps = []
         acc = None
         for i in range(args.warmup + args.steps):
-            r = time_reference(s, n_gpus, args.cpu_sample_iters)
+            r = time_reference(s, n_gpus, args.cpu_sample_iters, mh_std)
             acc = r["accept"]
             if i >= args.warmup:
                 steps.append(r)
@@ -231,26 +243,30 @@ def main():
     eng.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
     if args.mh_batch:
         eng.set_option("mh_batch", args.mh_batch)
+    if args.profile_phases:
+        eng.set_option("mh_profile", 1)
     ext = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     seed = 20261019
 
     for w in range(args.warmup):
-        eng.mh_launch(MH_ITR, MH_STD, seed, 1000 * rank + w)
+        eng.mh_launch(MH_ITR, mh_std, seed, 1000 * rank + w)
         eng.mh_wait(fetch=False)
     fp64_peak = P.fp64_peak(local_rank)                                 # DFMA thread-instr/s, measured on this GPU now
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     # ---- value: device-resident, CUDA events on the library's stream
     launches0 = eng.get_option("launches")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, ratios = [], []
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     with torch.cuda.stream(ext):
         e0.record(ext)
         for k in range(args.steps):
             flush.zero_()                                               # L2 flush between timed steps (inside the bracket)
-            eng.mh_launch(MH_ITR, MH_STD, seed, 1000 * rank + 100 + k)
+            eng.mh_launch(MH_ITR, mh_std, seed, 1000 * rank + 100 + k)
             r = eng.mh_wait(fetch=False)
             kernel_ms.append(r["kernel_ms"])
             ratios.append(r["ratio"])
@@ -269,11 +285,20 @@ def main():
     t0 = time.perf_counter()
     for k in range(args.steps):
         eng.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
-        eng.mh_run(MH_ITR, MH_STD, seed, 1000 * rank + 200 + k)
+        eng.mh_run(MH_ITR, mh_std, seed, 1000 * rank + 200 + k)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = n_gpus * args.steps * MH_ITR / e2e_s
 
+    if args.profile_phases and rank == 0:
+        names = ["likelihood", "publish", "speculative_draw", "barrier_wait", "reduce", "decide", "accept_path", "batches"]
+        pc = [eng.get_option("mh_prof_%d" % i) for i in range(8)]
+        tot = max(sum(pc[:7]), 1)
+        print("phase cycles (CTA 0, last launch): " + ", ".join("%s=%d (%.1f%%)" % (n, v, 100.0 * v / tot) for n, v in zip(names[:7], pc[:7]))
+              + ", batches=%d, cycles/batch=%.0f" % (pc[7], tot / max(pc[7], 1)), file=sys.stderr)
+        dn = ["gamma", "normalise", "subtree", "lgamma_log", "reduce_tail"]
+        dv = [eng.get_option("mh_prof_%d" % (8 + i)) for i in range(5)]
+        print("draw cycles per batch (warp 0): " + ", ".join("%s=%.0f" % (n, v / max(pc[7], 1)) for n, v in zip(dn, dv)), file=sys.stderr)
     if rank != 0:
         eng.close()
         if world > 1:
@@ -298,7 +323,7 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        r = time_reference(s, 1, args.cpu_sample_iters)
+        r = time_reference(s, 1, args.cpu_sample_iters, mh_std)
         cpu_baseline = {"value": r["rate"], "unit": UNIT, "cores": 1, "kind": "reference",
                         "sample": "oracle/_ref/mh.o (unmodified mh.cpp+util.cpp, g++ -O3, GSL shim) MH_ITR=%d on the same %s inputs: %.2fs total, "
                                   "%.2fs of it the per-call text re-parse (excluded from the rate); accept=%.4f; host has %d cores"

@@ -58,13 +58,22 @@ struct pwgs_ctx {
     int K = 0;
     DevBuf<int> parent, depth, tin, tout, order, node_of_datum;
     DevBuf<double> phi, pi;
-    DevBuf<int4> coef;
+    DevBuf<int4> coef;                                    // dense [K][M] coefficients, built only for pwgs_get_data_states
+    // sparse CNV work list of the MH kernel (rebuilt lazily after set_tree / when the CTA count changes)
+    int maxL = 0, work_cpc = -1;
+    bool work_valid = false;
+    DevBuf<int> code_tmp, enode_tmp, pos, w_a, w_d, w_code, w_enode, overflow;
+    DevBuf<int4> ecoef_tmp, w_ecoef;
+    DevBuf<double> w_lbc, w_mu_r;
+    CnvWork work;
     // ---- MH
-    DevBuf<double> partials, phi_out, pi_out, llh_out, scratch;
-    DevBuf<unsigned long long> counter;
-    DevBuf<int> acc_out, rows;
+    DevBuf<double> partials, ring, phi_out, pi_out, llh_out, scratch;
+    DevBuf<unsigned long long> counter, prof;
+    bool opt_prof = false;
+    unsigned long long prof_host[16] = {0};
+    DevBuf<int> acc_out, rows, abort_flag;
     DevBuf<MhParams> plist;
-    int opt_batch = 1, opt_ctas = 0, opt_block = 512;
+    int opt_batch = PWGS_MAX_BATCH, opt_ctas = 0, opt_stage = 1, opt_dist = -1;
     bool launched = false;
     int launched_iters = 0;
     long long n_launches = 0;                             // kernels of this library launched on behalf of the context
@@ -116,8 +125,10 @@ int pwgs_destroy(pwgs_ctx *c)
     c->pmu_r.release(); c->pmu_v.release(); c->cmu_r.release(); c->clbc.release();
     c->parent.release(); c->depth.release(); c->tin.release(); c->tout.release(); c->order.release(); c->node_of_datum.release();
     c->phi.release(); c->pi.release(); c->coef.release();
-    c->partials.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
-    c->counter.release(); c->acc_out.release(); c->rows.release(); c->plist.release();
+    c->code_tmp.release(); c->enode_tmp.release(); c->pos.release(); c->w_a.release(); c->w_d.release(); c->w_code.release();
+    c->w_enode.release(); c->overflow.release(); c->ecoef_tmp.release(); c->w_ecoef.release(); c->w_lbc.release(); c->w_mu_r.release();
+    c->partials.release(); c->ring.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
+    c->counter.release(); c->prof.release(); c->acc_out.release(); c->abort_flag.release(); c->rows.release(); c->plist.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -160,6 +171,7 @@ int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
     pwgs_ctx *c = new pwgs_ctx;
     c->device = device; c->n_sms = prop.multiProcessorCount;
     c->n_ssm = n_ssm; c->n_cnv = n_cnv; c->T = T; c->D = D; c->L = L;
+    if (cnv_ptr) for (int j = 0; j < n_ssm; j++) c->maxL = std::max(c->maxL, cnv_ptr[j + 1] - cnv_ptr[j]);
 #define CREATE_TRY(expr)                                                                              \
     do {                                                                                              \
         cudaError_t e_ = (expr);                                                                      \
@@ -235,6 +247,7 @@ int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
     CREATE_TRY(cudaStreamSynchronize(s));   // host staging vectors go out of scope below
     CREATE_TRY(c->counter.alloc(1));
     CREATE_TRY(c->acc_out.alloc(1));
+    CREATE_TRY(c->abort_flag.alloc(1));
     CREATE_TRY(c->llh_out.alloc(1));
     CREATE_TRY(c->plist.alloc(1));
 #undef CREATE_TRY
@@ -300,12 +313,7 @@ int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node
         c->n_launches++;
         CUDA_TRY(cudaGetLastError());
     }
-    CUDA_TRY(c->coef.alloc((size_t)std::max(c->M, 1) * K));
-    if (c->M > 0) {
-        data_states_kernel<<<(c->M + 127) / 128, 128, 0, s>>>(data_view(c), tree_view(c), c->M, c->cidx.p, c->coef.p);
-        c->n_launches++;
-        CUDA_TRY(cudaGetLastError());
-    }
+    c->work_valid = false;
     CUDA_TRY(cudaStreamSynchronize(s));   // host arrays (incl. local vectors) may go away after return
     c->tree_set = true;
     return PWGS_OK;
@@ -313,21 +321,47 @@ int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node
 
 } // extern "C"
 
-// ------------------------------------------------------------------ MH
-static size_t mh_smem_bytes(int K, int T, int B, int block)
+// ------------------------------------------------------------------ sparse CNV work list (K0c)
+static int prepare_cnv_work(pwgs_ctx *c, int cpc)
 {
-    size_t KT = (size_t)K * T, NW = block / 32;
-    size_t doubles = 4 * KT + T + 4 * (size_t)B * KT + 3 * (size_t)B * T + 2 * (size_t)B + (size_t)B * NW;
-    return doubles * sizeof(double) + 2 * (size_t)K * sizeof(int) + 16;
+    if (c->work_valid && c->work_cpc == cpc) return PWGS_OK;
+    const int M = c->M, T = c->T, K = c->K;
+    CnvWork &w = c->work;
+    w.Emax = std::max(1, std::min(K, c->maxL + 2));
+    w.cchunk = (M + cpc - 1) / cpc;
+    w.Mp = std::max(1, w.cchunk * cpc);
+    cudaStream_t s = c->stream;
+    CUDA_TRY(c->w_a.alloc((size_t)w.Mp * T)); CUDA_TRY(c->w_d.alloc((size_t)w.Mp * T)); CUDA_TRY(c->w_lbc.alloc((size_t)w.Mp * T));
+    CUDA_TRY(c->w_mu_r.alloc(w.Mp)); CUDA_TRY(c->w_code.alloc(w.Mp));
+    CUDA_TRY(c->w_enode.alloc((size_t)w.Mp * w.Emax)); CUDA_TRY(c->w_ecoef.alloc((size_t)w.Mp * w.Emax));
+    w.a = c->w_a.p; w.d = c->w_d.p; w.lbc = c->w_lbc.p; w.mu_r = c->w_mu_r.p; w.code = c->w_code.p; w.enode = c->w_enode.p; w.ecoef = c->w_ecoef.p;
+    if (M > 0) {
+        CUDA_TRY(c->code_tmp.alloc(M)); CUDA_TRY(c->pos.alloc(M)); CUDA_TRY(c->overflow.alloc(1));
+        CUDA_TRY(c->enode_tmp.alloc((size_t)M * w.Emax)); CUDA_TRY(c->ecoef_tmp.alloc((size_t)M * w.Emax));
+        CUDA_TRY(cudaMemsetAsync(c->overflow.p, 0, sizeof(int), s));
+        cnv_sparse_kernel<<<(M + 127) / 128, 128, 0, s>>>(data_view(c), tree_view(c), M, w.Emax, c->cidx.p, c->code_tmp.p, c->enode_tmp.p,
+                                                          c->ecoef_tmp.p, c->overflow.p);
+        CUDA_TRY(cudaGetLastError());
+        cnv_sort_kernel<<<1, 1024, 0, s>>>(M, c->code_tmp.p, c->pos.p);
+        CUDA_TRY(cudaGetLastError());
+        cnv_scatter_kernel<<<(M + 127) / 128, 128, 0, s>>>(M, T, cpc, w, c->pos.p, c->ca.p, c->cd.p, c->clbc.p, c->cmu_r.p, c->code_tmp.p,
+                                                           c->enode_tmp.p, c->ecoef_tmp.p);
+        CUDA_TRY(cudaGetLastError());
+        c->n_launches += 3;
+        int ovf = 0;
+        CUDA_TRY(cudaMemcpyAsync(&ovf, c->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (ovf) return fail(PWGS_ELIMIT, "internal: sparse CNV entry bound exceeded");
+    }
+    c->work_valid = true;
+    c->work_cpc = cpc;
+    return PWGS_OK;
 }
 
-template <int B>
-static cudaError_t launch_mh(const MhParams *plist, int cpc, int n_chains, int block, size_t smem, cudaStream_t s)
+// ------------------------------------------------------------------ MH
+static size_t mh_smem_bytes(int K, int T, int B)
 {
-    cudaError_t e = cudaFuncSetAttribute(mh_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    void *args[] = {(void *)&plist, (void *)&cpc};
-    return cudaLaunchCooperativeKernel((void *)mh_kernel<B>, dim3(n_chains * cpc), dim3(block), args, smem, s);
+    return mh_smem_doubles(K, T, B) * sizeof(double) + mh_smem_ints(K) * sizeof(int) + 16;
 }
 
 extern "C" {
@@ -340,38 +374,54 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     if (!(mh_std > 0)) return fail(PWGS_EINVAL, "mh_std must be > 0");
     CUDA_TRY(cudaSetDevice(c->device));
     int B = c->opt_batch;
-    int block = c->opt_block;
     int cpc = c->opt_ctas > 0 ? std::min(c->opt_ctas, c->n_sms) : c->n_sms;
-    size_t smem = mh_smem_bytes(c->K, c->T, B, block);
-    while (smem > 200 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B, block); }
+    size_t smem = mh_smem_bytes(c->K, c->T, B);
+    while (smem > 160 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B); }
     if (smem > 200 * 1024) return fail(PWGS_ELIMIT, "K*T too large for the shared-memory node table");
+    { int rc_ = prepare_cnv_work(c, cpc); if (rc_ != PWGS_OK) return rc_; }
+    // stage each CTA's slice of the data in shared memory when it fits beside the node tables
+    const size_t stage_bytes = mh_stage_bytes((c->Dp + cpc - 1) / cpc, c->work.cchunk, c->T, c->work.Emax) + 16;
+    const int stage = (c->opt_stage && smem + stage_bytes <= 224 * 1024) ? 1 : 0;
+    if (stage) smem += stage_bytes;
     CUDA_TRY(c->partials.alloc((size_t)2 * PWGS_MAX_BATCH * cpc));
+    CUDA_TRY(c->ring.alloc((size_t)MH_RING * mh_bufstride(c->K, c->T, B)));
+    const int distributed = c->opt_dist < 0 ? (cpc >= MH_DIST_MIN_CTAS ? 1 : 0) : c->opt_dist;
     CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->abort_flag.p, 0, sizeof(int), c->stream));
 
     MhParams p;
     p.Dp = c->Dp; p.M = c->M; p.T = c->T; p.K = c->K;
     p.pa = c->pa.p; p.pd = c->pd.p; p.pmu_r = c->pmu_r.p; p.pmu_v = c->pmu_v.p; p.pnode = c->pnode.p;
-    p.ca = c->ca.p; p.cd = c->cd.p; p.cmu_r = c->cmu_r.p; p.clbc = c->clbc.p; p.coef = c->coef.p;
-    p.parent = c->parent.p; p.order = c->order.p; p.phi0 = c->phi.p; p.pi0 = c->pi.p;
+    p.cw = c->work;
+    p.tin = c->tin.p; p.tout = c->tout.p; p.phi0 = c->phi.p; p.pi0 = c->pi.p;
     p.phi_out = c->phi_out.p; p.pi_out = c->pi_out.p; p.acc_out = c->acc_out.p; p.llh_out = c->llh_out.p;
-    p.iters = iters; p.mh_std = (double)(float)mh_std;   // mh.hpp:28: MH_STD is a float
+    p.iters = iters; p.max_batch = B; p.stage = stage; p.distributed = distributed; p.mh_std = (double)(float)mh_std;   // mh.hpp:28: MH_STD is a float
     p.seed = seed; p.stream = stream;
-    p.partials = c->partials.p; p.counter = c->counter.p;
-    p.lbc_plain_sum = c->lbc_plain_sum; p.log_tiny = kLogTinyMh; p.log_quarter = kLogQuarter;
+    p.partials = c->partials.p; p.ring = c->ring.p; p.counter = c->counter.p; p.abort_flag = c->abort_flag.p;
+    p.lbc_plain_sum = c->lbc_plain_sum; p.log_tiny = kLogTinyMh;
+    p.prof = nullptr;
+    if (c->opt_prof) { CUDA_TRY(c->prof.alloc(16)); p.prof = c->prof.p; }
     // pageable source: the runtime stages the bytes before returning, so the stack object is safe
     CUDA_TRY(cudaMemcpyAsync(c->plist.p, &p, sizeof(p), cudaMemcpyHostToDevice, c->stream));
 
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    cudaError_t e;
-    switch (B) {
-    case 1: e = launch_mh<1>(c->plist.p, cpc, 1, block, smem, c->stream); break;
-    case 2: e = launch_mh<2>(c->plist.p, cpc, 1, block, smem, c->stream); break;
-    case 4: e = launch_mh<4>(c->plist.p, cpc, 1, block, smem, c->stream); break;
-    case 8: e = launch_mh<8>(c->plist.p, cpc, 1, block, smem, c->stream); break;
-    case 16: e = launch_mh<16>(c->plist.p, cpc, 1, block, smem, c->stream); break;
-    default: return fail(PWGS_EINVAL, "mh_batch must be 1, 2, 4, 8 or 16");
+    cudaError_t e = cudaFuncSetAttribute(mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        const MhParams *plist = c->plist.p;
+        void *args[] = {(void *)&plist, (void *)&cpc};
+        e = cudaLaunchCooperativeKernel((void *)mh_kernel, dim3(cpc), dim3(MH_THREADS), args, smem, c->stream);
     }
-    if (e != cudaSuccess) return fail(PWGS_ECUDA, std::string("mh_kernel launch: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        cudaFuncAttributes fa;
+        int occ = -1;
+        cudaGetLastError();
+        cudaFuncGetAttributes(&fa, mh_kernel);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_kernel, MH_THREADS, smem);
+        return fail(PWGS_ECUDA, std::string("mh_kernel launch: ") + cudaGetErrorString(e) + " (grid " + std::to_string(cpc) + " x " +
+                    std::to_string(MH_THREADS) + " threads, " + std::to_string(smem) + " B dynamic smem, " + std::to_string(fa.numRegs) +
+                    " regs, maxThreadsPerBlock " + std::to_string(fa.maxThreadsPerBlock) + ", static smem " + std::to_string(fa.sharedSizeBytes) +
+                    ", local " + std::to_string(fa.localSizeBytes) + ", occupancy " + std::to_string(occ) + " CTA/SM)");
+    }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->n_launches++;
     c->launched = true;
@@ -386,13 +436,16 @@ int pwgs_mh_wait(pwgs_ctx *c, double *phi_out, double *pi_out, double *accept_ra
     CUDA_TRY(cudaSetDevice(c->device));
     c->launched = false;
     size_t KT = (size_t)c->K * c->T;
-    int acc = 0;
+    int acc = 0, aborted = 0;
     double llh = 0;
     if (phi_out) CUDA_TRY(cudaMemcpyAsync(phi_out, c->phi_out.p, KT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (pi_out) CUDA_TRY(cudaMemcpyAsync(pi_out, c->pi_out.p, KT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(&acc, c->acc_out.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(&aborted, c->abort_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(&llh, c->llh_out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (c->opt_prof && c->prof.p) CUDA_TRY(cudaMemcpyAsync(c->prof_host, c->prof.p, sizeof(c->prof_host), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (aborted) return fail(PWGS_ECUDA, "MH kernel watchdog: the chain barrier did not complete (kernel aborted itself)");
     if (accept_ratio) *accept_ratio = c->launched_iters > 0 ? (double)acc / c->launched_iters : 0.0;   // mh.cpp:104-107
     if (llh_out) *llh_out = llh;
     if (kernel_ms) CUDA_TRY(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
@@ -469,6 +522,10 @@ int pwgs_get_data_states(pwgs_ctx *c, int32_t *M, int32_t *ssm_of_m, int32_t *co
     if (ssm_of_m) for (int m = 0; m < c->M; m++) ssm_of_m[m] = c->ssm_of_m[m];
     if (coef && c->M > 0) {
         CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(c->coef.alloc((size_t)c->M * c->K));
+        data_states_kernel<<<(c->M + 127) / 128, 128, 0, c->stream>>>(data_view(c), tree_view(c), c->M, c->cidx.p, c->coef.p);
+        CUDA_TRY(cudaGetLastError());
+        c->n_launches++;
         std::vector<int4> h((size_t)c->M * c->K);
         CUDA_TRY(cudaMemcpyAsync(h.data(), c->coef.p, h.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -496,9 +553,13 @@ int pwgs_set_option(pwgs_ctx *c, const char *name, int64_t value)
     } else if (n == "mh_ctas") {
         if (value < 0) return fail(PWGS_EINVAL, "mh_ctas must be >= 0");
         c->opt_ctas = (int)value;
-    } else if (n == "mh_block") {
-        if (value < 64 || value > 512 || value % 32) return fail(PWGS_EINVAL, "mh_block must be a multiple of 32 in 64..512");
-        c->opt_block = (int)value;
+    } else if (n == "mh_dist") {
+        if (value < -1 || value > 1) return fail(PWGS_EINVAL, "mh_dist must be -1 (auto), 0 or 1");
+        c->opt_dist = (int)value;
+    } else if (n == "mh_stage") {
+        c->opt_stage = value != 0;
+    } else if (n == "mh_profile") {
+        c->opt_prof = value != 0;
     } else return fail(PWGS_EINVAL, "unknown option " + n);
     return PWGS_OK;
 }
@@ -509,11 +570,12 @@ int pwgs_get_option(pwgs_ctx *c, const char *name, int64_t *value)
     std::string n(name);
     if (n == "mh_batch") *value = c->opt_batch;
     else if (n == "mh_ctas") *value = c->opt_ctas;
-    else if (n == "mh_block") *value = c->opt_block;
     else if (n == "n_sms") *value = c->n_sms;
     else if (n == "n_plain") *value = c->Dp;
     else if (n == "n_cnv_ssm") *value = c->M;
     else if (n == "launches") *value = c->n_launches;
+    else if (n.rfind("mh_prof_", 0) == 0 && n.size() == 9 && n[8] >= '0' && n[8] <= '9') *value = (int64_t)c->prof_host[n[8] - '0'];
+    else if (n.rfind("mh_prof_1", 0) == 0 && n.size() == 10 && n[9] >= '0' && n[9] <= '5') *value = (int64_t)c->prof_host[10 + n[9] - '0'];
     else return fail(PWGS_EINVAL, "unknown option " + n);
     return PWGS_OK;
 }

@@ -71,6 +71,230 @@ __device__ __forceinline__ void state_coefs(const DataView &d, const TreeView &t
     }
 }
 
+// ------------------------------------------------------------------ straight-line fp64 log / exp
+// The MH kernel evaluates up to eight independent logarithms per datum.  CUDA's log()/exp() carry slow-path branches that
+// keep the compiler from interleaving neighbouring calls; these versions are branch-free (special cases are selects at the
+// end), so independent calls overlap in the FP64 pipe.  Accuracy < 1 ulp (same argument reduction and minimax coefficients
+// as Sun's fdlibm e_log.c, a published algorithm; not GSL, not the reference).
+__device__ __forceinline__ double pwgs_rcp_approx(double d)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    return y;
+}
+
+__device__ __forceinline__ double pwgs_log(double x)
+{
+    int hi = __double2hiint(x), lo = __double2loint(x);
+    const bool sub = hi < 0x00100000;                        // subnormal (or <= 0: fixed up below)
+    const double xs = x * 18014398509481984.0;               // 2^54
+    hi = sub ? __double2hiint(xs) : hi;
+    lo = sub ? __double2loint(xs) : lo;
+    int e = (sub ? -54 : 0) + (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int i = (hi + 0x95f64) & 0x100000;                 // mantissa >= sqrt(2): halve it, bump the exponent
+    hi |= i ^ 0x3ff00000;
+    e += i >> 20;
+    const double f = __hiloint2double(hi, lo) - 1.0;         // m - 1, m in [sqrt(2)/2, sqrt(2))
+    const double d = 2.0 + f;
+    double y = pwgs_rcp_approx(d);                           // ~2^-20; two Newton steps -> full precision
+    double t = fma(-d, y, 1.0);
+    y = fma(y, t, y);
+    t = fma(-d, y, 1.0);
+    y = fma(y, t, y);
+    double q = f * y;
+    q = fma(fma(-d, q, f), y, q);                            // s = f / (2 + f), correctly rounded to < 1 ulp
+    const double z = q * q, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
+    double r = fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(q, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+    r = (x == 0.0) ? -INFINITY : r;
+    r = (x < 0.0 || x != x) ? NAN : r;
+    r = (x == INFINITY) ? INFINITY : r;
+    return r;
+}
+
+// log(x) for NORMAL POSITIVE FINITE x only (no zero / negative / subnormal / inf / nan handling): the binomial means mu and
+// 1 - mu of the likelihood, which pwgs_create / pwgs_set_tree keep strictly inside (0, 1).  Same arithmetic as pwgs_log.
+__device__ __forceinline__ double pwgs_log_pos(double x)
+{
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int i = (hi + 0x95f64) & 0x100000;
+    hi |= i ^ 0x3ff00000;
+    e += i >> 20;
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double d = 2.0 + f;
+    double y = pwgs_rcp_approx(d);
+    double t = fma(-d, y, 1.0);
+    y = fma(y, t, y);
+    t = fma(-d, y, 1.0);
+    y = fma(y, t, y);
+    double q = f * y;
+    q = fma(fma(-d, q, f), y, q);
+    const double z = q * q, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
+    return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(q, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+}
+
+// N independent pwgs_log_pos evaluations written step by step across the N values, so that the instruction stream the
+// compiler emits alternates between the N dependency chains (it does not interleave N separate inlined calls on its own, and a
+// single chain leaves the FP64 pipe idle for most of its latency).
+template <int N>
+__device__ __forceinline__ void pwgs_log_pos_n(const double (&x)[N], double (&r)[N])
+{
+    double f[N], d[N], y[N], t[N], q[N], z[N], w[N], t1[N], t2[N], dk[N], hf[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        int hi = __double2hiint(x[i]);
+        const int lo = __double2loint(x[i]);
+        int e = (hi >> 20) - 1023;
+        hi &= 0x000fffff;
+        const int k = (hi + 0x95f64) & 0x100000;
+        hi |= k ^ 0x3ff00000;
+        e += k >> 20;
+        dk[i] = (double)e;
+        f[i] = __hiloint2double(hi, lo) - 1.0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) d[i] = 2.0 + f[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = pwgs_rcp_approx(d[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = fma(-d[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = fma(-d[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = f[i] * y[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = fma(-d[i], q[i], f[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) q[i] = fma(t[i], y[i], q[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) z[i] = q[i] * q[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) w[i] = z[i] * z[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t1[i] = fma(w[i], 1.531383769920937332e-01, 2.222219843214978396e-01);
+#pragma unroll
+    for (int i = 0; i < N; i++) t2[i] = fma(w[i], 1.479819860511658591e-01, 1.818357216161805012e-01);
+#pragma unroll
+    for (int i = 0; i < N; i++) t1[i] = fma(w[i], t1[i], 3.999999999940941908e-01);
+#pragma unroll
+    for (int i = 0; i < N; i++) t2[i] = fma(w[i], t2[i], 2.857142874366239149e-01);
+#pragma unroll
+    for (int i = 0; i < N; i++) t1[i] = w[i] * t1[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t2[i] = fma(w[i], t2[i], 6.666666666666735130e-01);
+#pragma unroll
+    for (int i = 0; i < N; i++) hf[i] = 0.5 * f[i] * f[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t2[i] = fma(z[i], t2[i], t1[i]);                                  // R
+#pragma unroll
+    for (int i = 0; i < N; i++) t1[i] = dk[i] * 1.90821492927058770002e-10;
+#pragma unroll
+    for (int i = 0; i < N; i++) t2[i] = fma(q[i], hf[i] + t2[i], t1[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) t2[i] = (hf[i] - t2[i]) - f[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(dk[i], 6.93147180369123816490e-01, -t2[i]);
+}
+
+// N independent a[i] / b[i], b > 0 (see pwgs_div_pos)
+template <int N>
+__device__ __forceinline__ void pwgs_div_pos_n(const double (&a)[N], const double (&b)[N], double (&r)[N])
+{
+    double y[N], t[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = pwgs_rcp_approx(b[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = fma(-b[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = fma(-b[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = a[i] * y[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = fma(-b[i], r[i], a[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(t[i], y[i], r[i]);
+}
+
+// exp(x) for x <= 0 (arguments of logsumexp after the max shift).  Arguments below -700 are clamped: the callers add the
+// result to a sum that already holds exp(0) = 1, so anything below 1e-300 rounds away exactly as a true 0 would.
+__device__ __forceinline__ double pwgs_exp_nonpos(double x)
+{
+    x = fmax(x, -700.0);
+    double kd = fma(x, 1.4426950408889634074, 6755399441055744.0);   // round(x / ln2) in the low mantissa bits
+    const int n = __double2loint(kd);
+    kd -= 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);                      // |r| <= ln2/2
+    double p = 1.6059043836821613e-10;                                // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                              // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                             // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                             // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                            // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                              // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                             // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);                             // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                             // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                            // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                            // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));   // * 2^n, n >= -1010: stays normal
+}
+
+// N independent pwgs_exp_nonpos evaluations, interleaved like pwgs_log_pos_n
+template <int N>
+__device__ __forceinline__ void pwgs_exp_nonpos_n(const double (&xin)[N], double (&out)[N])
+{
+    double x[N], kd[N], r[N], p[N];
+    int n[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = fmax(xin[i], -700.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) kd[i] = fma(x[i], 1.4426950408889634074, 6755399441055744.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) { n[i] = __double2loint(kd[i]); kd[i] -= 6755399441055744.0; }
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(kd[i], -6.93147180369123816490e-01, x[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(kd[i], -1.90821492927058770002e-10, r[i]);
+    const double c[13] = {2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+                          2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03,
+                          4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = 1.6059043836821613e-10;
+#pragma unroll
+    for (int j = 0; j < 13; j++) {
+#pragma unroll
+        for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], c[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) out[i] = __hiloint2double(__double2hiint(p[i]) + (n[i] << 20), __double2loint(p[i]));
+}
+
+// log(w/4) and log(w) for state multiplicities w = 0..4 (index 0 unused)
+__constant__ double c_logw4[5] = {0.0, -1.3862943611198906, -0.6931471805599453, -0.2876820724517809, 0.0};
+__constant__ double c_logw[5] = {0.0, 0.0, 0.6931471805599453, 1.0986122886681098, 1.3862943611198906};
+
 // ------------------------------------------------------------------ likelihood terms
 // util.cpp:16-18 / util2.py:30
 __device__ __forceinline__ double log_binomial_likelihood(int x, int n, double mu)
@@ -140,7 +364,8 @@ __device__ __forceinline__ void stream_draw(uint64_t seed, uint64_t stream, uint
 __device__ __forceinline__ double philox_gamma(double alpha, uint64_t seed, uint64_t stream, uint32_t it, uint32_t node, uint32_t tp)
 {
     double d = alpha - 1.0 / 3.0, c = (1.0 / 3.0) / sqrt(d);
-    for (uint32_t j = 0;; j++) {
+    // the attempt cap only guards against a non-finite alpha (never reached otherwise: each attempt succeeds with p > 0.95)
+    for (uint32_t j = 0; j < 4096u; j++) {
         double u0, u1, ua, ub;
         stream_draw(seed, stream, it, node, tp, PWGS_PURPOSE_GAMMA, 2 * j, u0, u1);
         double x = sqrt(-2.0 * log(u0)) * cospi(2.0 * u1);
@@ -151,6 +376,7 @@ __device__ __forceinline__ double philox_gamma(double alpha, uint64_t seed, uint
         if (ua < 1.0 - 0.0331 * x * x * x * x) return d * v;
         if (log(ua) < 0.5 * x * x + d * (1.0 - v + log(v))) return d * v;
     }
+    return d;
 }
 
 // ------------------------------------------------------------------ reductions / sync

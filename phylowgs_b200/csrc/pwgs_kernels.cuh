@@ -75,6 +75,146 @@ __global__ void data_states_kernel(DataView dv, TreeView tv, int M, const int *_
     }
 }
 
+// ============================================================================ K0c  sparse CNV work list for the MH kernel
+// For a CNV-affected SSM the state coefficients c[q][k] of params.py:114-171 are piecewise constant over the tree: they depend
+// on node k only through "is k under the SSM's node" and "which linked CNV is the most recent one above k".  Writing
+// c[q][k] = sum over ancestors-or-self a of k of delta[q][a] gives  sum_k pi_k c[q][k] = sum_a delta[q][a] * phi_a  (phi = subtree
+// sums, mh.cpp:134-141), and delta is non-zero only at the root, at the SSM's node and at nodes hosting one of its CNVs:
+// <= 2 + (#links) entries instead of K.  States that coincide on every node (st3 == st4 always; st1 == st2 == st3 for most
+// 2-state SSMs) are merged into one "unique state" with a multiplicity, so  logsumexp_q(ll_q) = logsumexp_u(ll_u + log w_u).
+//
+// code[m]: bits 0..7 number of entries, bits 8..9 number of unique states (1..3), bits 12..14 / 16..18 / 20..22 multiplicities.
+#define CNV_CODE(ne, nu, w0, w1, w2) ((ne) | ((nu) << 8) | ((w0) << 12) | ((w1) << 16) | ((w2) << 20))
+
+__device__ __forceinline__ void final_state_coefs(const DataView &dv, const TreeView &tv, int j, int s, int k, bool sub0, bool sub1,
+                                                  bool four, int nr[4], int nv[4])
+{
+    state_coefs(dv, tv, j, s, k, nr, nv);
+    if (sub0) { nr[0] = nr[1]; nv[0] = nv[1]; }                       // params.py:160-161
+    else if (sub1) { nr[1] = nr[0]; nv[1] = nv[0]; }                  // params.py:162-163
+    if (!four) { nr[2] = nr[0]; nv[2] = nv[0]; nr[3] = nr[1]; nv[3] = nv[1]; }   // params.py:164-166
+}
+
+// One thread per CNV-affected SSM m (input order).  Writes code[m] and up to Emax entries (enode, ecoef) at [e*M + m];
+// ecoef packs (nr,nv) deltas of unique states 0..2 as int16 pairs in x,y,z.  *overflow is set if an SSM needs more entries.
+__global__ void cnv_sparse_kernel(DataView dv, TreeView tv, int M, int Emax, const int *__restrict__ ssm_of_m,
+                                  int *__restrict__ code, int *__restrict__ enode, int4 *__restrict__ ecoef, int *overflow)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int j = ssm_of_m[m], s = tv.node_of_datum[j], K = tv.K;
+    double pv0 = 0, pv1 = 0;
+    for (int k = 0; k < K; k++) {
+        int nr[4], nv[4];
+        state_coefs(dv, tv, j, s, k, nr, nv);
+        double p = tv.pi[k * tv.T];
+        pv0 += p * nv[0];
+        pv1 += p * nv[1];
+    }
+    const bool sub0 = pv0 == 0, sub1 = !sub0 && pv1 == 0;
+    const bool four = (dv.cnv_ptr[j + 1] - dv.cnv_ptr[j] == 1) && (s == tv.node_of_datum[dv.n_ssm + dv.cnv_idx[dv.cnv_ptr[j]]]);
+    bool e01 = true, e02 = true, e12 = true;                           // state 3 always equals state 2 (or state 1 when !four)
+    for (int k = 0; k < K; k++) {
+        int nr[4], nv[4];
+        final_state_coefs(dv, tv, j, s, k, sub0, sub1, four, nr, nv);
+        e01 &= nr[0] == nr[1] && nv[0] == nv[1];
+        e02 &= nr[0] == nr[2] && nv[0] == nv[2];
+        e12 &= nr[1] == nr[2] && nv[1] == nv[2];
+    }
+    // unique states in first-occurrence order with multiplicities over the four states {0,1,2,3}; 3 mirrors 2 when four, else 1
+    int uq[3] = {0, -1, -1}, w[3] = {1, 0, 0}, nu = 1;
+    int rep1 = e01 ? 0 : 1;
+    if (rep1 == 1) { uq[nu] = 1; w[nu] = 1; nu++; } else w[0]++;
+    int rep2 = e02 ? 0 : (e12 ? 1 : 2);
+    int twice = 2;                                                     // states 2 and 3 coincide (st3 == st4 / mirrored pair below)
+    if (!four) {
+        // 2-state SSM: state 2 := state 0, state 3 := state 1
+        w[0] += 1;
+        if (rep1 == 1) w[1] += 1; else w[0] += 1;
+    } else {
+        if (rep2 == 2) { uq[nu] = 2; w[nu] = twice; nu++; }
+        else if (rep2 == 0) w[0] += twice;
+        else w[1] += twice;                                            // rep2 == 1 implies rep1 == 1: unique index 1 is state 1
+    }
+    int ne = 0;
+    for (int k = 0; k < K; k++) {
+        int nr[4], nv[4], pr[4] = {0, 0, 0, 0}, pvv[4] = {0, 0, 0, 0};
+        final_state_coefs(dv, tv, j, s, k, sub0, sub1, four, nr, nv);
+        if (tv.parent[k] >= 0) final_state_coefs(dv, tv, j, s, tv.parent[k], sub0, sub1, four, pr, pvv);
+        int d[3] = {0, 0, 0};
+        bool any = false;
+        for (int u = 0; u < nu; u++) {
+            int q = uq[u];
+            int dr = nr[q] - pr[q], dvv = nv[q] - pvv[q];
+            d[u] = (dr & 0xffff) | (dvv << 16);
+            any |= (dr != 0) || (dvv != 0);
+        }
+        if (any) {
+            if (ne < Emax) {
+                enode[(size_t)ne * M + m] = k;
+                ecoef[(size_t)ne * M + m] = make_int4(d[0], d[1], d[2], 0);
+            } else *overflow = 1;
+            ne++;
+        }
+    }
+    code[m] = CNV_CODE(min(ne, Emax), nu, w[0], w[1], w[2]);
+}
+
+// Stable 3-bucket counting sort of the CNV-affected SSMs by their number of unique states, most expensive first (single CTA,
+// deterministic): pos[m] = rank of m in the sorted order.  Warps of the MH kernel then see (nearly) uniform work per round and
+// the partially filled last warp of a CTA holds the cheapest SSMs.
+__global__ void cnv_sort_kernel(int M, const int *__restrict__ code, int *__restrict__ pos)
+{
+    __shared__ int cnt[1024][3];
+    __shared__ int base[3];
+    const int t = threadIdx.x, per = (M + blockDim.x - 1) / blockDim.x, lo = min(M, t * per), hi = min(M, lo + per);
+    int c[3] = {0, 0, 0};
+    for (int m = lo; m < hi; m++) c[3 - ((code[m] >> 8) & 3)]++;
+    cnt[t][0] = c[0]; cnt[t][1] = c[1]; cnt[t][2] = c[2];
+    __syncthreads();
+    if (t == 0) {
+        int run[3] = {0, 0, 0};
+        for (int i = 0; i < (int)blockDim.x; i++)
+            for (int b = 0; b < 3; b++) { int v = cnt[i][b]; cnt[i][b] = run[b]; run[b] += v; }
+        base[0] = 0; base[1] = run[0]; base[2] = run[0] + run[1];
+    }
+    __syncthreads();
+    int o[3] = {base[0] + cnt[t][0], base[1] + cnt[t][1], base[2] + cnt[t][2]};
+    for (int m = lo; m < hi; m++) pos[m] = o[3 - ((code[m] >> 8) & 3)]++;
+}
+
+// Scatter into the CTA-major layout the MH kernel streams: sorted rank r goes to CTA r % cpc, local slot r / cpc, i.e.
+// index (r % cpc) * cchunk + r / cpc, so every CTA gets the same mix of cheap and expensive SSMs, contiguous and sorted.
+struct CnvWork {
+    int *a, *d;            // [T][Mp]
+    double *lbc;           // [T][Mp]
+    double *mu_r;          // [Mp]
+    int *code;             // [Mp]
+    int *enode;            // [Emax][Mp]
+    int4 *ecoef;           // [Emax][Mp]
+    int Mp, cchunk, Emax;
+};
+__global__ void cnv_scatter_kernel(int M, int T, int cpc, CnvWork w, const int *__restrict__ pos, const int *__restrict__ ca,
+                                   const int *__restrict__ cd, const double *__restrict__ clbc, const double *__restrict__ cmu_r,
+                                   const int *__restrict__ code, const int *__restrict__ enode, const int4 *__restrict__ ecoef)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int r = pos[m], dst = (r % cpc) * w.cchunk + r / cpc;
+    for (int tp = 0; tp < T; tp++) {
+        w.a[(size_t)tp * w.Mp + dst] = ca[(size_t)tp * M + m];
+        w.d[(size_t)tp * w.Mp + dst] = cd[(size_t)tp * M + m];
+        w.lbc[(size_t)tp * w.Mp + dst] = clbc[(size_t)tp * M + m];
+    }
+    w.mu_r[dst] = cmu_r[m];
+    const int cd_ = code[m];
+    w.code[dst] = cd_;
+    for (int e = 0; e < (cd_ & 0xff); e++) {
+        w.enode[(size_t)e * w.Mp + dst] = enode[(size_t)e * M + m];
+        w.ecoef[(size_t)e * w.Mp + dst] = ecoef[(size_t)e * M + m];
+    }
+}
+
 // ============================================================================ K2
 // llh of datum j placed in node s under either convention (see oracle/pwgs_oracle.c datum_ll_cpp_at / orc_datum_ll_py).
 __device__ double datum_ll_at(const DataView &dv, const TreeView &tv, int j, int s, int semantics,
@@ -169,249 +309,679 @@ __global__ void sum_kernel(int n, const double *__restrict__ x, double *out)
 }
 
 // ============================================================================ K1
+#define MH_CWARPS 8                      // consumer warps (likelihood + bookkeeping): 2 per SM sub-partition, 224 registers each,
+                                         // so that 8 chains of fp64 logarithms per thread stay in registers and overlap
+#define MH_CONSUMERS (MH_CWARPS * 32)
+#define MH_THREADS (MH_CONSUMERS + 32)   // + one producer warp (proposal draws for the ring)
+#define MH_BU 4                          // proposals evaluated per thread in one pass over its data
+#define MH_RING 4                        // slots of the global proposal ring
+#define MH_WATCHDOG_CYCLES 8000000000ll  // ~4 s of SM clock: a barrier that has not completed by then never will
+#define MH_DIST_MIN_CTAS 32              // chains with fewer CTAs draw every proposal locally in every CTA
+
 struct MhParams {
     int Dp, M, T, K;
     const int *pa, *pd;                 // [T][Dp]  plain data (SSMs outside CNVs + CNV data), sample-major
     const double *pmu_r, *pmu_v;        // [Dp]
     const int *pnode;                   // [Dp] node index of each plain datum
-    const int *ca, *cd;                 // [T][M]  CNV-affected SSMs
-    const double *cmu_r;                // [M]
-    const double *clbc;                 // [T][M]
-    const int4 *coef;                   // [K][M]  8 x int16 state coefficients
-    const int *parent, *order;          // [K]; order = nodes by (depth desc, index asc)
+    CnvWork cw;                         // CNV-affected SSMs: sorted, CTA-major sparse work list (K0c)
+    const int *tin, *tout;              // [K] Euler-tour interval of every node (subtree test)
     const double *phi0, *pi0;           // [K*T] state on entry
     double *phi_out, *pi_out;           // [K*T] state on exit
     int *acc_out;                       // accepted proposals
     double *llh_out;                    // multi_param_post of the final state
-    int iters;
+    int iters, max_batch;               // max_batch: power of two in 1..16
+    int stage;                          // 1: each CTA copies its slice of the data into shared memory once (normal case)
+    int distributed;                    // 1: proposals two batches ahead are drawn once per chain and shared through `ring`
     double mh_std;
     unsigned long long seed, stream;
-    double *partials;                   // [2][B][cpc]
+    double *partials;                   // [2][PWGS_MAX_BATCH][cpc]
+    double *ring;                       // [MH_RING][bufstride] proposal ring (distributed mode)
     unsigned long long *counter;        // arrival counter of the chain's grid barrier (zeroed before launch)
-    double lbc_plain_sum, log_tiny, log_quarter;
+    int *abort_flag;                    // watchdog: set when a spin wait exceeds MH_WATCHDOG_CYCLES; every CTA then leaves the loop
+    double lbc_plain_sum, log_tiny;
+    unsigned long long *prof;           // optional [16] cycle counters of CTA 0 / thread 0 (NULL = off)
 };
 
-// One chain = cpc co-resident CTAs (cooperative launch).  Every CTA holds the full node table in shared
-// memory, generates the SAME proposals from the counter-based stream (no broadcast needed), evaluates its
-// slice of the data for B speculative proposals at once, and the partial sums meet in a per-chain barrier.
-// B > 1 is "prefetching" MH: proposals for iterations it0..it0+B-1 are all drawn from the current state; the
-// first accepted one ends the batch and later ones are discarded, which is exactly the sequential chain because
-// a rejected iteration leaves the state untouched and each iteration owns its random substream.
-template <int B>
-__global__ void __launch_bounds__(512, 1) mh_kernel(const MhParams *__restrict__ plist, int cpc)
+// ---- shared-memory carve-up of one CTA (doubles first, then ints, then the staged data slice)
+struct MhSmem {
+    // two copies of the chain state (an accept writes the other copy, so the producer warp never reads a half-written one)
+    double *state0;                                 // per copy: pi[KT], phi[KT], log(pi)[KT], lgamma(std*pi)[KT], lgsum[T], slg[T]
+    int statestride, KT, T;
+    __device__ __forceinline__ double *pi(int e) const { return state0 + e * statestride; }
+    __device__ __forceinline__ double *phi(int e) const { return state0 + e * statestride + KT; }
+    __device__ __forceinline__ double *lp(int e) const { return state0 + e * statestride + 2 * KT; }
+    __device__ __forceinline__ double *lg(int e) const { return state0 + e * statestride + 3 * KT; }
+    __device__ __forceinline__ double *lgsum(int e) const { return state0 + e * statestride + 4 * KT; }
+    __device__ __forceinline__ double *slg(int e) const { return state0 + e * statestride + 4 * KT + T; }
+    // two proposal buffers (current batch / next batch), `bufstride` doubles apart; the ring slots use the same layout
+    double *buf0;                                   // per buffer: pi1[MAXB*KT], phi1[MAXB*KT], hastings[MAXB*T], log r[MAXB]
+    int bufstride, o_phi, o_hast, o_logr;
+    __device__ __forceinline__ double *prop_pi(int b) const { return buf0 + b * bufstride; }
+    __device__ __forceinline__ double *prop_phi(int b) const { return buf0 + b * bufstride + o_phi; }
+    __device__ __forceinline__ double *hast(int b) const { return buf0 + b * bufstride + o_hast; }
+    __device__ __forceinline__ double *logr(int b) const { return buf0 + b * bufstride + o_logr; }
+    double *red;                                    // [MH_BU][MH_CWARPS]
+    double *llh;                                    // [MAXB]
+    double *pscratch;                               // [2K] producer warp: pi1 and phi1 of the proposal being drawn
+    volatile int *ctl;                              // producer mailbox, see MhCtl
+    int *tin, *tout;                                // [K]
+};
+enum MhCtl { CTL_GEN = 0, CTL_DONE = 1, CTL_PROD_DONE = 2, CTL_ABORT = 3, CTL_JOB = 4 /* 2 x {state, it, nb} */, CTL_WORDS = 12 };
+
+__host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return 2 * (size_t)maxb * K * T + (size_t)maxb * T + maxb; }
+__host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
 {
-    extern __shared__ double sm[];
+    size_t KT = (size_t)K * T;
+    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + MH_BU * MH_CWARPS + maxb + 2 * K;
+}
+__host__ __device__ inline size_t mh_smem_ints(int K) { return CTL_WORDS + 2 * (size_t)K; }
+
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MH_CONSUMERS) : "memory"); }
+__device__ __forceinline__ int pow2_floor(int x) { return x <= 0 ? 0 : 1 << (31 - __clz(x)); }
+// size of the batch that follows a batch of n rejected proposals, with `left` iterations still to do
+__device__ __forceinline__ int next_batch(int n, int left, int maxb) { return pow2_floor(min(min(maxb, 2 * n), left)); }
+
+// single out-of-line copy of the (large) lgamma routine
+__device__ __noinline__ double pwgs_lgamma(double x) { return lgamma(x); }
+
+// One warp draws proposal `it` for sample tp from chain state copy e: pi1 ~ Dirichlet(mh_std*pi + 1) -> +1e-4 -> renormalise
+// (mh.cpp:113-131, util.cpp:24-33), phi1 = subtree sums of pi1 (mh.cpp:134-141) and the Hastings correction of mh.cpp:80-93
+// for this sample; for tp == 0 also the log of the iteration's acceptance uniform (mh.cpp:95-96).  Lanes own the nodes
+// k = lane, lane+32, ...; every reduction is a fixed-shape shuffle tree, so all CTAs of a chain get bit-identical results.
+// x / ph: pi1 / phi1 of node k at [k * xs].
+__device__ __noinline__ void mh_propose(const MhParams &p, const MhSmem &S, int e, double *x, double *ph, int xs, double *hast_out,
+                                        double *logr_out, int tp, uint32_t it, int lane)
+{
+    const int T = p.T, K = p.K;
+    const double mstd = p.mh_std;
+    const double *cpi = S.pi(e), *clp = S.lp(e);
+    double s = 0.0;
+#pragma unroll 1
+    for (int k = lane; k < K; k += 32) {
+        double g = philox_gamma(mstd * cpi[k * T + tp] + 1.0, p.seed, p.stream, it, (uint32_t)k, (uint32_t)tp);
+        x[k * xs] = g;
+        s += g;
+    }
+    const double norm = warp_sum(s);                                             // gsl_ran_dirichlet normalisation
+    s = 0.0;
+#pragma unroll 1
+    for (int k = lane; k < K; k += 32) {
+        double v = x[k * xs] / norm + 0.0001;                                    // util.cpp:26-27
+        x[k * xs] = v;
+        s += v;
+    }
+    const double sum = warp_sum(s);                                              // util.cpp:28-30
+    double sa = 0.0;
+#pragma unroll 1
+    for (int k = lane; k < K; k += 32) {
+        double v = x[k * xs] / sum;                                              // util.cpp:31-32
+        x[k * xs] = v;
+        sa += mstd * v;
+    }
+    const double sa1 = warp_sum(sa);
+    __syncwarp();
+    double t1 = 0.0, t2 = 0.0, slg = 0.0, lgs = 0.0;
+#pragma unroll 1
+    for (int k = lane; k <= K; k += 32) {                                        // virtual node K: lgamma(sum alpha) rides along
+        const bool real = k < K;
+        const int kk = real ? k : 0;
+        const int lo = S.tin[kk], hi = S.tout[kk];
+        double acc = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < K; j++) {                                            // phi_k = sum of pi over the subtree of k
+            double v = x[j * xs];
+            if (lo <= S.tin[j] && S.tout[j] <= hi) acc += v;
+        }
+        if (real) ph[k * xs] = acc;
+        const double pn = real ? x[kk * xs] : 1.0, pv = cpi[kk * T + tp];
+        const double lg = pwgs_lgamma(real ? mstd * pn : sa1), lpn = log(pn);
+        if (real) {
+            t1 += (mstd * pn - 1.0) * clp[k * T + tp];                           // lnDir(pi ; mh_std*pi1), mh.cpp:86-88
+            slg += lg;
+            t2 += (mstd * pv - 1.0) * lpn;                                       // lnDir(pi1 ; mh_std*pi), mh.cpp:90-92
+        } else lgs = lg;
+    }
+    t1 = warp_sum(t1); t2 = warp_sum(t2); slg = warp_sum(slg); lgs = warp_sum(lgs);
+    if (lane == 0) {
+        double lp1 = t1 + lgs - slg;
+        double lp2 = t2 + S.lgsum(e)[tp] - S.slg(e)[tp];
+        *hast_out = lp1 - lp2;
+        if (tp == 0) {
+            double u0, u1;
+            stream_draw(p.seed, p.stream, it, 0, 0, PWGS_PURPOSE_ACCEPT, 0, u0, u1);
+            *logr_out = log(u0);
+        }
+    }
+}
+
+// the consumer warps draw a whole batch (nb proposals x T samples) into proposal buffer `buf`
+__device__ __forceinline__ void mh_draw_local(const MhParams &p, const MhSmem &S, int e, int buf, int nb, int it_first, int warp, int lane)
+{
+    const int T = p.T, KT = p.K * T;
+#pragma unroll 1
+    for (int task = warp; task < nb * T; task += MH_CWARPS) {
+        const int b = task / T, tp = task - b * T;
+        mh_propose(p, S, e, S.prop_pi(buf) + b * KT + tp, S.prop_phi(buf) + b * KT + tp, T, S.hast(buf) + b * T + tp,
+                   S.logr(buf) + b, tp, (uint32_t)(it_first + b), lane);
+    }
+}
+
+// log(pi), lgamma(mh_std*pi) and their per-sample sums for state copy e (consumer warps; caller syncs before and after)
+__device__ __noinline__ void mh_refresh_state(const MhParams &p, const MhSmem &S, int e, int tid, int warp, int lane)
+{
+    const int T = p.T, K = p.K, KT = K * T;
+#pragma unroll 1
+    for (int i = tid; i < KT; i += MH_CONSUMERS) {
+        S.lp(e)[i] = log(S.pi(e)[i]);
+        S.lg(e)[i] = pwgs_lgamma(p.mh_std * S.pi(e)[i]);
+    }
+    consumer_sync();
+#pragma unroll 1
+    for (int tp = warp; tp < T; tp += MH_CWARPS) {
+        double sa = 0.0, sl = 0.0;
+#pragma unroll 1
+        for (int k = lane; k < K; k += 32) { sa += p.mh_std * S.pi(e)[k * T + tp]; sl += S.lg(e)[k * T + tp]; }
+        sa = warp_sum(sa); sl = warp_sum(sl);
+        if (lane == 0) { S.lgsum(e)[tp] = pwgs_lgamma(sa); S.slg(e)[tp] = sl; }
+    }
+}
+
+// a / b for b > 0 without the slow-path branch of the IEEE division (|error| <= 1 ulp)
+__device__ __forceinline__ double pwgs_div_pos(double a, double b)
+{
+    double y = pwgs_rcp_approx(b);
+    double t = fma(-b, y, 1.0);
+    y = fma(y, t, y);
+    t = fma(-b, y, 1.0);
+    y = fma(y, t, y);
+    double q = a * y;
+    return fma(fma(-b, q, a), y, q);
+}
+
+// ---- the CTA's slice of the two work lists as the likelihood loop reads it: element l of the slice lives at [tp * stride + l].
+// Normally the slice is staged in shared memory once per launch (SliceShared: offsets into the dynamic shared array, so the
+// loads are LDS); slices too large for shared memory are read in place from global memory (SliceGlobal).
+extern __shared__ __align__(16) double mh_sm[];
+struct SliceShared {
+    int np, pstride, nc, cstride;
+    int o_pint, o_pdbl, o_cint, o_cdbl, o_ecoef;       // offsets in elements of int / double / int / double / int4
+    int T;
+    __device__ __forceinline__ double pmu_r(int i) const { return mh_sm[o_pdbl + i]; }
+    __device__ __forceinline__ double pmu_v(int i) const { return mh_sm[o_pdbl + pstride + i]; }
+    __device__ __forceinline__ int pnode(int i) const { return ((const int *)mh_sm)[o_pint + i]; }
+    __device__ __forceinline__ int pa(int tp, int i) const { return ((const int *)mh_sm)[o_pint + (1 + tp) * pstride + i]; }
+    __device__ __forceinline__ int pd(int tp, int i) const { return ((const int *)mh_sm)[o_pint + (1 + T + tp) * pstride + i]; }
+    __device__ __forceinline__ double cmu_r(int i) const { return mh_sm[o_cdbl + i]; }
+    __device__ __forceinline__ double clbc(int tp, int i) const { return mh_sm[o_cdbl + (1 + tp) * cstride + i]; }
+    __device__ __forceinline__ int ccode(int i) const { return ((const int *)mh_sm)[o_cint + i]; }
+    __device__ __forceinline__ int ca(int tp, int i) const { return ((const int *)mh_sm)[o_cint + (1 + tp) * cstride + i]; }
+    __device__ __forceinline__ int cd(int tp, int i) const { return ((const int *)mh_sm)[o_cint + (1 + T + tp) * cstride + i]; }
+    __device__ __forceinline__ int cenode(int e, int i) const { return ((const int *)mh_sm)[o_cint + (1 + 2 * T + e) * cstride + i]; }
+    __device__ __forceinline__ int cecoef(int e, int i, int u) const { return ((const int *)mh_sm)[4 * (o_ecoef + e * cstride + i) + u]; }
+};
+struct SliceGlobal {
+    int np, pstride, nc, cstride;
+    const int *g_pa, *g_pd, *g_pnode, *g_ca, *g_cd, *g_ccode, *g_cenode;
+    const double *g_pmu_r, *g_pmu_v, *g_clbc, *g_cmu_r;
+    const int4 *g_cecoef;
+    __device__ __forceinline__ double pmu_r(int i) const { return __ldg(g_pmu_r + i); }
+    __device__ __forceinline__ double pmu_v(int i) const { return __ldg(g_pmu_v + i); }
+    __device__ __forceinline__ int pnode(int i) const { return __ldg(g_pnode + i); }
+    __device__ __forceinline__ int pa(int tp, int i) const { return __ldg(g_pa + (size_t)tp * pstride + i); }
+    __device__ __forceinline__ int pd(int tp, int i) const { return __ldg(g_pd + (size_t)tp * pstride + i); }
+    __device__ __forceinline__ double cmu_r(int i) const { return __ldg(g_cmu_r + i); }
+    __device__ __forceinline__ double clbc(int tp, int i) const { return __ldg(g_clbc + (size_t)tp * cstride + i); }
+    __device__ __forceinline__ int ccode(int i) const { return __ldg(g_ccode + i); }
+    __device__ __forceinline__ int ca(int tp, int i) const { return __ldg(g_ca + (size_t)tp * cstride + i); }
+    __device__ __forceinline__ int cd(int tp, int i) const { return __ldg(g_cd + (size_t)tp * cstride + i); }
+    __device__ __forceinline__ int cenode(int e, int i) const { return __ldg(g_cenode + (size_t)e * cstride + i); }
+    __device__ __forceinline__ int cecoef(int e, int i, int u) const { return __ldg((const int *)(g_cecoef + (size_t)e * cstride + i) + u); }
+};
+
+__host__ __device__ inline size_t mh_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+// bytes of shared memory for a staged slice of pchunk plain data and cchunk CNV-affected SSMs
+__host__ __device__ inline size_t mh_stage_bytes(int pchunk, int cchunk, int T, int Emax)
+{
+    size_t b = 0;
+    b += mh_align16((size_t)cchunk * Emax * sizeof(int4));
+    b += mh_align16((size_t)pchunk * 2 * sizeof(double)) + mh_align16((size_t)cchunk * (1 + (size_t)T) * sizeof(double));
+    b += mh_align16((size_t)pchunk * (1 + 2 * (size_t)T) * sizeof(int)) + mh_align16((size_t)cchunk * (1 + 2 * (size_t)T + Emax) * sizeof(int));
+    return b;
+}
+
+// Likelihood of this CTA's slice of the data for the nb proposals of the batch (param_post, mh.cpp:153-166).  The consumer
+// warps are split into nb/BU groups; group g evaluates proposals g*BU .. g*BU+BU-1, each thread walking the CTA's data with
+// the group's stride and accumulating BU sums, so that every load / int->fp64 conversion is shared by BU proposals and the BU
+// independent chains of logarithms overlap in the FP64 pipe.  Leaves red[bb][warp] = the warp's sum for proposal g*BU+bb.
+template <int BU, class Slice>
+__device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S, const Slice &sl, int cur, int nb, int warp, int lane)
+{
+    const int T = p.T, KT = p.K * T;
+    // group g = warps [g*wpg, (g+1)*wpg); inside a group the warp roles are rotated by g so that the warps holding the expensive
+    // head of the sorted CNV list land on different SM sub-partitions (warp id % 4) in different groups
+    const int wpg = MH_CWARPS / (nb / BU), tpg = wpg * 32, g = warp / wpg;
+    const int lt = ((warp - g * wpg + g) % wpg) * 32 + lane;
+    const double *bphi = S.prop_phi(cur) + (g * BU) * KT;
+    double acc[BU];
+#pragma unroll
+    for (int bb = 0; bb < BU; bb++) acc[bb] = 0.0;
+
+    // ---- CNV-affected SSMs (mh.hpp:90-161) through the sparse, state-merged work list
+    const int cnt = sl.nc;
+#pragma unroll 1
+    for (int l = lt; l - lane < cnt; l += tpg) {
+        const bool act = l < cnt;
+        const int idx = act ? l : 0;
+        const int code = act ? sl.ccode(idx) : 0;
+        const int ne = code & 0xff, nu = (code >> 8) & 3;
+        const int numax = __reduce_max_sync(PWGS_FULL_MASK, nu);
+        const double mu_r = sl.cmu_r(idx), omr = 1.0 - mu_r;
+#pragma unroll 1
+        for (int tp = 0; tp < T; tp++) {
+            const int a = sl.ca(tp, idx), d = sl.cd(tp, idx);
+            const double lbc = sl.clbc(tp, idx), fa = (double)a, fb = (double)(d - a);
+            // states one after the other with a running (max, sum) pair: util.cpp:35-43 over the merged states
+            double mx[BU], sm[BU];
+#pragma unroll 1
+            for (int u = 0; u < numax; u++) {                                    // warp-uniform trip count
+                double nr[BU], nv[BU];
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) nr[bb] = nv[bb] = 0.0;
+#pragma unroll 1
+                for (int e = 0; e < ne; e++) {
+                    const int node = sl.cenode(e, idx) * T + tp;
+                    const int cu = sl.cecoef(e, idx, u);
+                    const double dr = (double)(short)(cu & 0xffff), dv = (double)(cu >> 16);
+#pragma unroll
+                    for (int bb = 0; bb < BU; bb++) {
+                        const double ph = bphi[bb * KT + node];
+                        nr[bb] = fma(ph, dr, nr[bb]);
+                        nv[bb] = fma(ph, dv, nv[bb]);
+                    }
+                }
+                const int w = (code >> (12 + 4 * u)) & 7;
+                const double lw = lbc + c_logw4[w], tiny = p.log_tiny + c_logw[w];
+                double num[BU], den[BU], mu[BU], om[BU];
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) {
+                    den[bb] = nr[bb] + nv[bb];
+                    num[bb] = fma(nv[bb], omr, nr[bb] * mu_r);
+                }
+                pwgs_div_pos_n<BU>(num, den, mu);                                                              // mh.hpp:96
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) { mu[bb] = den[bb] > 0.0 ? mu[bb] : 0.5; om[bb] = 1.0 - mu[bb]; }
+                double xx[2 * BU], ll[2 * BU];
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) { xx[bb] = mu[bb]; xx[BU + bb] = om[bb]; }
+                pwgs_log_pos_n<2 * BU>(xx, ll);
+                double val[BU];
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) {
+                    val[bb] = fma(fa, ll[bb], fma(fb, ll[BU + bb], lw));
+                    val[bb] = u < nu ? (den[bb] > 0.0 ? val[bb] : tiny) : -INFINITY;                           // mh.hpp:95-101
+                }
+                if (u == 0) {
+#pragma unroll
+                    for (int bb = 0; bb < BU; bb++) { mx[bb] = val[bb]; sm[bb] = 1.0; }
+                } else {
+                    double nm[BU], x1[BU], x2[BU];
+#pragma unroll
+                    for (int bb = 0; bb < BU; bb++) { nm[bb] = fmax(mx[bb], val[bb]); x1[bb] = mx[bb] - nm[bb]; x2[bb] = val[bb] - nm[bb]; }
+                    double xe[2 * BU], ee[2 * BU];
+#pragma unroll
+                    for (int bb = 0; bb < BU; bb++) { xe[bb] = x1[bb]; xe[BU + bb] = x2[bb]; }
+                    pwgs_exp_nonpos_n<2 * BU>(xe, ee);
+#pragma unroll
+                    for (int bb = 0; bb < BU; bb++) { sm[bb] = fma(sm[bb], ee[bb], ee[BU + bb]); mx[bb] = nm[bb]; }
+                }
+            }
+            if (numax <= 1) {
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) acc[bb] += act ? mx[bb] : 0.0;
+            } else {
+                double ls[BU];
+                pwgs_log_pos_n<BU>(sm, ls);
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) acc[bb] += act ? mx[bb] + ls[bb] : 0.0;
+            }
+        }
+    }
+
+    // ---- plain data (mh.hpp:86-89): SSMs outside CNVs and the CNV data themselves
+#pragma unroll 1
+    for (int j = lt; j - lane < sl.np; j += tpg) {
+        const bool act = j < sl.np;
+        const int jj = act ? j : 0;
+        const double mu_r = sl.pmu_r(jj), mu_v = sl.pmu_v(jj);
+        const int nodeT = sl.pnode(jj) * T;
+#pragma unroll 1
+        for (int tp = 0; tp < T; tp++) {
+            const int a = sl.pa(tp, jj), d = sl.pd(tp, jj);
+            const double fa = act ? (double)a : 0.0, fb = act ? (double)(d - a) : 0.0;
+            double xx[2 * BU], ll[2 * BU];
+#pragma unroll
+            for (int bb = 0; bb < BU; bb++) {
+                const double phi = bphi[bb * KT + nodeT + tp];
+                xx[bb] = (1.0 - phi) * mu_r + phi * mu_v;
+                xx[BU + bb] = 1.0 - xx[bb];
+            }
+            pwgs_log_pos_n<2 * BU>(xx, ll);
+#pragma unroll
+            for (int bb = 0; bb < BU; bb++) acc[bb] += fa * ll[bb] + fb * ll[BU + bb];
+        }
+    }
+#pragma unroll
+    for (int bb = 0; bb < BU; bb++) {
+        const double t = warp_sum(acc[bb]);
+        if (lane == 0) S.red[bb * MH_CWARPS + warp] = t;
+    }
+}
+
+// ---- the producer warp: draws the proposals this CTA owns of the batch two ahead and posts them in the global ring
+__device__ __noinline__ void mh_producer(const MhParams &p, const MhSmem &S, int rank, int cpc, int lane)
+{
+    const int T = p.T, K = p.K, KT = K * T;
+    const size_t slot_doubles = mh_bufstride(K, T, p.max_batch);
+    int job = 1;                                                                // jobs are numbered by global batch, from 1
+#pragma unroll 1
+    for (;;) {
+        while (S.ctl[CTL_GEN] < job && !S.ctl[CTL_DONE]) { }
+        if (S.ctl[CTL_GEN] < job) return;                                        // done and nothing new posted
+        __threadfence_block();
+        const volatile int *jb = S.ctl + CTL_JOB + 3 * (job & 1);
+        const int e = jb[0], it_first = jb[1], nb = jb[2];
+        double *slot = p.ring + (size_t)((job + 2) % MH_RING) * slot_doubles;
+#pragma unroll 1
+        for (int task = 0; task < nb * T; task++) {
+            if ((task + job * 37) % cpc != rank) continue;                       // one owner CTA per (proposal, sample)
+            const int b = task / T, tp = task - b * T;
+            double hast = 0.0, logr = 0.0;
+            mh_propose(p, S, e, S.pscratch, S.pscratch + K, 1, &hast, &logr, tp, (uint32_t)(it_first + b), lane);
+            __syncwarp();
+#pragma unroll 1
+            for (int k = lane; k < K; k += 32) {
+                slot[(size_t)b * KT + k * T + tp] = S.pscratch[k];
+                slot[(size_t)S.o_phi + (size_t)b * KT + k * T + tp] = S.pscratch[K + k];
+            }
+            if (lane == 0) {
+                slot[(size_t)S.o_hast + b * T + tp] = hast;
+                if (tp == 0) slot[(size_t)S.o_logr + b] = logr;
+            }
+            __syncwarp();
+        }
+        __threadfence();                                                         // ring stores ordered before the "done" flag
+        __syncwarp();
+        if (lane == 0) S.ctl[CTL_PROD_DONE] = job;
+        job++;
+    }
+}
+
+// One chain = cpc co-resident CTAs (cooperative launch).  Every CTA keeps the node table in shared memory, evaluates its slice
+// of the data for a batch of nb speculative proposals, and the per-CTA partial sums meet in a per-chain barrier.
+// "Prefetching" MH: proposals for iterations it0..it0+nb-1 are all drawn from the current state; the first accepted one ends
+// the batch and the later ones are discarded, which is exactly the sequential chain because a rejected iteration leaves the
+// state untouched and each iteration owns its random substream.  The batch size adapts to the acceptance rate (doubling after
+// all-reject batches, shrinking after accepts).  Proposals are drawn ahead of time under the assumption that the batches in
+// flight reject everything: the first two batches after every accept are drawn redundantly by every CTA (the second one while
+// the first one's barrier is in flight); from the third on, each (proposal, sample) is drawn ONCE per chain by the producer
+// warp of its owner CTA two batches ahead and travels through a ring in global memory under the chain barrier's release /
+// acquire.  Chains with few CTAs keep drawing locally.
+__global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, int cpc)
+{
+    double *sm = mh_sm;
     __shared__ MhParams p;                              // this chain's descriptor (grid = n_chains * cpc CTAs)
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = nthr >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = blockIdx.x % cpc;
     if (tid == 0) p = plist[blockIdx.x / cpc];
     __syncthreads();
-    const int T = p.T, K = p.K, KT = K * T;
-    const double mstd = p.mh_std;
+    const int T = p.T, K = p.K, KT = K * T, MAXB = p.max_batch;
+    const bool dist = p.distributed != 0;
 
-    double *cur_pi = sm, *cur_phi = cur_pi + KT, *cur_lg = cur_phi + KT, *cur_lp = cur_lg + KT, *cur_lgsum = cur_lp + KT;
-    double *prop_pi = cur_lgsum + T, *prop_phi = prop_pi + B * KT, *prop_lg = prop_phi + B * KT, *prop_lp = prop_lg + B * KT;
-    double *prop_lgsum = prop_lp + B * KT;              // [B*T]
-    double *L1 = prop_lgsum + B * T, *L2 = L1 + B * T;  // [B*T] each
-    double *logr = L2 + B * T, *llh = logr + B;         // [B] each
-    double *red = llh + B;                              // [B*NW]
-    int *s_parent = (int *)(red + B * NW), *s_order = s_parent + K;
-    __shared__ int s_sel;
-
-    for (int e = tid; e < KT; e += nthr) {
-        cur_pi[e] = p.pi0[e];
-        cur_phi[e] = p.phi0[e];
-        cur_lp[e] = log(cur_pi[e]);
-        cur_lg[e] = lgamma(mstd * cur_pi[e]);
-        prop_pi[e] = cur_pi[e];                         // slot 0 carries the entry state through the first pass
-        prop_phi[e] = cur_phi[e];
+    MhSmem S;
+    {
+        double *q = sm;
+        S.KT = KT; S.T = T; S.statestride = 4 * KT + 2 * T;
+        S.state0 = q; q += 2 * S.statestride;
+        S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = MAXB * KT; S.o_hast = 2 * MAXB * KT; S.o_logr = 2 * MAXB * KT + MAXB * T;
+        S.buf0 = q; q += 2 * S.bufstride;
+        S.red = q; q += MH_BU * MH_CWARPS; S.llh = q; q += MAXB;
+        S.pscratch = q; q += 2 * K;
+        S.ctl = (volatile int *)q; S.tin = (int *)q + CTL_WORDS; S.tout = S.tin + K;
     }
-    for (int k = tid; k < K; k += nthr) { s_parent[k] = p.parent[k]; s_order[k] = p.order[k]; }
-    __syncthreads();
-    if (tid < T) {
-        double sa = 0;
-        for (int k = 0; k < K; k++) sa += mstd * cur_pi[k * T + tid];
-        cur_lgsum[tid] = lgamma(sa);
+    for (int i = tid; i < KT; i += MH_THREADS) {
+        S.pi(0)[i] = p.pi0[i];
+        S.phi(0)[i] = p.phi0[i];
+        S.prop_pi(0)[i] = p.pi0[i];                    // slot 0 of buffer 0 carries the entry state through the first pass
+        S.prop_phi(0)[i] = p.phi0[i];
     }
+    for (int k = tid; k < K; k += MH_THREADS) { S.tin[k] = p.tin[k]; S.tout[k] = p.tout[k]; }
+    if (tid < CTL_WORDS) S.ctl[tid] = 0;
 
-    // this CTA's slices of the two work lists
+    // this CTA's slices of the plain work list (contiguous) and of the CNV work list (already CTA-major)
     const int pchunk = (p.Dp + cpc - 1) / cpc, p0 = min(p.Dp, rank * pchunk), p1 = min(p.Dp, p0 + pchunk);
-    const int cchunk = (p.M + cpc - 1) / cpc, c0 = min(p.M, rank * cchunk), c1 = min(p.M, c0 + cchunk);
-
-    int it0 = 0, accepted = 0;
-    unsigned long long barrier_no = 0;
-    double cur_llh = 0;
-    bool initial = true;
-
-    while (initial || it0 < p.iters) {
-        const int nb = initial ? 1 : min(B, p.iters - it0);
-        if (!initial) {
-            // ---------------- proposal: pi1 ~ Dirichlet(mh_std*pi + 1) per sample (mh.cpp:113-142, util.cpp:24-33)
-            for (int idx = tid; idx < nb * KT; idx += nthr) {
-                int b = idx / KT, e = idx - b * KT, k = e / T, tp = e - k * T;
-                double alpha = mstd * cur_pi[e] + 1.0;
-                prop_pi[idx] = philox_gamma(alpha, p.seed, p.stream, (uint32_t)(it0 + b), (uint32_t)k, (uint32_t)tp);
-            }
-            if (tid < nb) {
-                double u0, u1;
-                stream_draw(p.seed, p.stream, (uint32_t)(it0 + tid), 0, 0, PWGS_PURPOSE_ACCEPT, 0, u0, u1);
-                logr[tid] = log(u0);                                                 // mh.cpp:95-96
-            }
-            __syncthreads();
-            for (int idx = tid; idx < nb * T; idx += nthr) {
-                int b = idx / T, tp = idx - b * T;
-                double *x = prop_pi + b * KT + tp, *ph = prop_phi + b * KT + tp;
-                double norm = 0.0;
-                for (int k = 0; k < K; k++) norm += x[k * T];
-                for (int k = 0; k < K; k++) x[k * T] /= norm;                       // gsl_ran_dirichlet normalisation
-                for (int k = 0; k < K; k++) x[k * T] = x[k * T] + 0.0001;           // util.cpp:26-27
-                double sum = 0.0;
-                for (int k = 0; k < K; k++) sum += x[k * T];                         // util.cpp:28-30
-                for (int k = 0; k < K; k++) { x[k * T] /= sum; ph[k * T] = x[k * T]; }   // util.cpp:31-32
-                for (int i = 0; i < K; i++) {                                        // mh.cpp:134-141 (children first)
-                    int n = s_order[i], par = s_parent[n];
-                    if (par >= 0) ph[par * T] += ph[n * T];
-                }
-            }
-            __syncthreads();
-            // ---------------- pieces of the Hastings correction (mh.cpp:80-93)
-            for (int idx = tid; idx < nb * KT; idx += nthr) {
-                prop_lp[idx] = log(prop_pi[idx]);
-                prop_lg[idx] = lgamma(mstd * prop_pi[idx]);
-            }
-            __syncthreads();
-            for (int idx = tid; idx < nb * T; idx += nthr) {
-                int b = idx / T, tp = idx - b * T;
-                const double *pn = prop_pi + b * KT + tp, *lpn = prop_lp + b * KT + tp, *lgn = prop_lg + b * KT + tp;
-                // gsl_ran_dirichlet_lnpdf(K, theta = MH_STD*pi_new, pi)
-                double lp1 = 0.0, sa1 = 0.0;
-                for (int k = 0; k < K; k++) lp1 += (mstd * pn[k * T] - 1.0) * cur_lp[k * T + tp];
-                for (int k = 0; k < K; k++) sa1 += mstd * pn[k * T];
-                double lgs = lgamma(sa1);
-                lp1 += lgs;
-                for (int k = 0; k < K; k++) lp1 -= lgn[k * T];
-                // gsl_ran_dirichlet_lnpdf(K, theta = MH_STD*pi, pi_new)
-                double lp2 = 0.0;
-                for (int k = 0; k < K; k++) lp2 += (mstd * cur_pi[k * T + tp] - 1.0) * lpn[k * T];
-                lp2 += cur_lgsum[tp];
-                for (int k = 0; k < K; k++) lp2 -= cur_lg[k * T + tp];
-                L1[idx] = lp1; L2[idx] = lp2; prop_lgsum[idx] = lgs;
-            }
-            __syncthreads();
-        }
-
-        // ---------------- likelihood of this CTA's slice for all B proposals (param_post, mh.cpp:153-166)
-        double acc[B];
-#pragma unroll
-        for (int b = 0; b < B; b++) acc[b] = 0.0;
-        for (int j = p0 + tid; j < p1; j += nthr) {                                  // plain data: mh.hpp:86-89
-            double mu_r = p.pmu_r[j], mu_v = p.pmu_v[j];
-            int nodeT = p.pnode[j] * T;
+    const CnvWork &cw = p.cw;
+    const int cbase = rank * cw.cchunk, np = p1 - p0, nc = (p.M - rank + cpc - 1) / cpc;
+    SliceShared ss;
+    SliceGlobal sg;
+    if (p.stage) {
+        // carve the staging area behind the node tables (16-byte aligned) and copy the slice once
+        char *q = (char *)(S.tout + K);
+        q = (char *)mh_align16((size_t)q);
+        int4 *s_ecoef = (int4 *)q; q += mh_align16((size_t)cw.cchunk * cw.Emax * sizeof(int4));
+        double *s_pmu = (double *)q; q += mh_align16((size_t)pchunk * 2 * sizeof(double));
+        double *s_cd = (double *)q; q += mh_align16((size_t)cw.cchunk * (1 + (size_t)T) * sizeof(double));
+        int *s_pi = (int *)q; q += mh_align16((size_t)pchunk * (1 + 2 * (size_t)T) * sizeof(int));
+        int *s_ci = (int *)q;
+        for (int i = tid; i < np; i += MH_THREADS) {
+            s_pmu[i] = p.pmu_r[p0 + i]; s_pmu[pchunk + i] = p.pmu_v[p0 + i]; s_pi[i] = p.pnode[p0 + i];
             for (int tp = 0; tp < T; tp++) {
-                int a = p.pa[(size_t)tp * p.Dp + j], d = p.pd[(size_t)tp * p.Dp + j];
-                double fa = (double)a, fb = (double)(d - a);
-#pragma unroll
-                for (int b = 0; b < B; b++) {
-                    double phi = prop_phi[b * KT + nodeT + tp];
-                    double mu = (1.0 - phi) * mu_r + phi * mu_v;
-                    acc[b] += fa * log(mu) + fb * log(1.0 - mu);
-                }
+                s_pi[(1 + tp) * pchunk + i] = p.pa[(size_t)tp * p.Dp + p0 + i];
+                s_pi[(1 + T + tp) * pchunk + i] = p.pd[(size_t)tp * p.Dp + p0 + i];
             }
         }
-        for (int m = c0 + tid; m < c1; m += nthr) {                                  // CNV-affected SSMs: mh.hpp:90-161
-            double mu_r = p.cmu_r[m];
+        const int cc = cw.cchunk;
+        for (int i = tid; i < nc; i += MH_THREADS) {
+            s_cd[i] = cw.mu_r[cbase + i];
+            const int code = cw.code[cbase + i];
+            s_ci[i] = code;
             for (int tp = 0; tp < T; tp++) {
-                int a = p.ca[(size_t)tp * p.M + m], d = p.cd[(size_t)tp * p.M + m];
-                double lbc = p.clbc[(size_t)tp * p.M + m];
-#pragma unroll 1
-                for (int b = 0; b < B; b++) {
-                    const double *ppi = prop_pi + b * KT + tp;
-                    double nr[4] = {0, 0, 0, 0}, nv[4] = {0, 0, 0, 0};
-                    for (int k = 0; k < K; k++) {
-                        int4 c = __ldg(&p.coef[(size_t)k * p.M + m]);
-                        double pk = ppi[k * T];
-                        nr[0] += pk * (double)(short)(c.x & 0xffff); nv[0] += pk * (double)(c.x >> 16);
-                        nr[1] += pk * (double)(short)(c.y & 0xffff); nv[1] += pk * (double)(c.y >> 16);
-                        nr[2] += pk * (double)(short)(c.z & 0xffff); nv[2] += pk * (double)(c.z >> 16);
-                        nr[3] += pk * (double)(short)(c.w & 0xffff); nv[3] += pk * (double)(c.w >> 16);
-                    }
-                    double ll[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) ll[q] = mh_state_ll(nr[q], nv[q], a, d, mu_r, lbc, p.log_quarter, p.log_tiny);
-                    acc[b] += logsumexp4(ll);
-                }
+                s_cd[(1 + tp) * cc + i] = cw.lbc[(size_t)tp * cw.Mp + cbase + i];
+                s_ci[(1 + tp) * cc + i] = cw.a[(size_t)tp * cw.Mp + cbase + i];
+                s_ci[(1 + T + tp) * cc + i] = cw.d[(size_t)tp * cw.Mp + cbase + i];
+            }
+            for (int e = 0; e < (code & 0xff); e++) {
+                s_ci[(1 + 2 * T + e) * cc + i] = cw.enode[(size_t)e * cw.Mp + cbase + i];
+                s_ecoef[(size_t)e * cc + i] = cw.ecoef[(size_t)e * cw.Mp + cbase + i];
             }
         }
-        // ---------------- block reduction (fixed order) ...
-#pragma unroll
-        for (int b = 0; b < B; b++) {
-            double v = warp_sum(acc[b]);
-            if (lane == 0) red[b * NW + warp] = v;
-        }
-        __syncthreads();
-        const int parity = (int)(barrier_no & 1);
-        if (warp == 0) {
-            if (lane < B) {
-                double t = 0;
-                for (int w = 0; w < NW; w++) t += red[lane * NW + w];
-                p.partials[((size_t)parity * B + lane) * cpc + rank] = t;
-            }
-            __syncwarp();
-            // ---------------- ... and the chain-wide barrier: arrive (release), spin (acquire)
-            if (lane == 0) {
-                red_release_add(p.counter, 1ull);
-                unsigned long long target = (barrier_no + 1) * (unsigned long long)cpc;
-                while (ld_acquire(p.counter) < target) { }
-            }
-            __syncwarp();
-            // every CTA sums the same partials in the same order -> bit-identical decisions everywhere
-            for (int b = 0; b < nb; b++) {
-                double t = 0;
-                for (int r = lane; r < cpc; r += 32) t += __ldcg(&p.partials[((size_t)parity * B + b) * cpc + r]);
-                t = warp_sum(t);
-                if (lane == 0) llh[b] = t;
-            }
-            __syncwarp();
-            // ---------------- accept / reject (mh.cpp:73-100)
-            if (lane == 0) {
-                if (initial) {
-                    cur_llh = llh[0];
-                    s_sel = -2;
-                } else {
-                    int sel = -1;
-                    for (int b = 0; b < nb; b++) {
-                        double a = llh[b] - cur_llh;
-                        for (int tp = 0; tp < T; tp++) { a += L1[b * T + tp]; a -= L2[b * T + tp]; }
-                        if (logr[b] < a) { sel = b; break; }
-                    }
-                    s_sel = sel;
-                }
-            }
-        }
-        barrier_no++;
-        __syncthreads();
-        const int sel = s_sel;
-        if (initial) {
-            initial = false;
-        } else if (sel >= 0) {                                    // update_params, mh.cpp:170-177
-            for (int e = tid; e < KT; e += nthr) {
-                cur_pi[e] = prop_pi[sel * KT + e];
-                cur_phi[e] = prop_phi[sel * KT + e];
-                cur_lg[e] = prop_lg[sel * KT + e];
-                cur_lp[e] = prop_lp[sel * KT + e];
-            }
-            if (tid < T) cur_lgsum[tid] = prop_lgsum[sel * T + tid];
-            if (tid == 0) cur_llh = llh[sel];
-            accepted++;
-            it0 += sel + 1;
-        } else {
-            it0 += nb;
-        }
-        __syncthreads();
+        ss.np = np; ss.pstride = pchunk; ss.nc = nc; ss.cstride = cc; ss.T = T;
+        ss.o_ecoef = (int)(((char *)s_ecoef - (char *)sm) / 16); ss.o_pdbl = (int)(s_pmu - sm); ss.o_cdbl = (int)(s_cd - sm);
+        ss.o_pint = (int)(s_pi - (int *)sm); ss.o_cint = (int)(s_ci - (int *)sm);
+    } else {
+        sg.np = np; sg.pstride = p.Dp; sg.nc = nc; sg.cstride = cw.Mp;
+        sg.g_pmu_r = p.pmu_r + p0; sg.g_pmu_v = p.pmu_v + p0; sg.g_pnode = p.pnode + p0; sg.g_pa = p.pa + p0; sg.g_pd = p.pd + p0;
+        sg.g_cmu_r = cw.mu_r + cbase; sg.g_clbc = cw.lbc + cbase; sg.g_ccode = cw.code + cbase; sg.g_ca = cw.a + cbase;
+        sg.g_cd = cw.d + cbase; sg.g_cenode = cw.enode + cbase; sg.g_cecoef = cw.ecoef + cbase;
     }
+    __syncthreads();
+
+    if (warp == MH_CWARPS) {                           // ---- producer warp
+        if (dist) mh_producer(p, S, rank, cpc, lane);
+        return;
+    }
+
+    // =================================================================== consumer warps
+    mh_refresh_state(p, S, 0, tid, warp, lane);
+    consumer_sync();
+
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = clock64();
+#define MH_PROF(slot) do { if (prof) { long long t_ = clock64(); pc[slot] += (unsigned long long)(t_ - t_prev); t_prev = t_; } } while (0)
+
+    int e = 0;                                         // live copy of the chain state
+    int cur = 0;                                       // proposal buffer of the current batch
+    int b_it = 0, b_nb = 1;                            // current batch: first iteration, size
+    int j = -1;                                        // batches since the last accept; -1: the initial evaluation of the entry state
+    int accepted = 0;
+    int g = 0;                                         // global batch number == barrier number
+    double cur_llh = 0.0;
+
+#pragma unroll 1
+    while (b_nb > 0) {
+        // the batches that follow if everything is rejected
+        const int n1_it = j < 0 ? 0 : b_it + b_nb;
+        const int n1_nb = j < 0 ? pow2_floor(min(1, p.iters)) : next_batch(b_nb, p.iters - n1_it, MAXB);
+        const int n2_it = n1_it + n1_nb, n2_nb = next_batch(n1_nb, p.iters - n2_it, MAXB);
+        if (dist && tid == 0 && g >= 1) {              // post job g: draw batch g+2 from state copy e
+            volatile int *jb = S.ctl + CTL_JOB + 3 * (g & 1);
+            jb[0] = e; jb[1] = n2_it; jb[2] = n2_nb;
+            __threadfence_block();
+            S.ctl[CTL_GEN] = g;
+        }
+
+        // ---------------- likelihood (param_post) of the CTA's slice for every proposal of the batch
+        const int bu = b_nb >= MH_BU ? MH_BU : 1;      // thread groups of MH_BU proposals, or one proposal per group
+        if (p.stage) {
+            if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, ss, cur, b_nb, warp, lane); else mh_likelihood<1>(p, S, ss, cur, b_nb, warp, lane);
+        } else {
+            if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sg, cur, b_nb, warp, lane); else mh_likelihood<1>(p, S, sg, cur, b_nb, warp, lane);
+        }
+        consumer_sync();
+        MH_PROF(0);
+
+        // ---------------- publish the CTA's partial sums and arrive at the chain barrier (release)
+        const int parity = g & 1;
+        if (warp == 0) {
+            if (lane < b_nb) {
+                const int wpg = MH_CWARPS / (b_nb / bu), gg = lane / bu, bb = lane - gg * bu;     // warps per thread group
+                double t = 0.0;
+                for (int w2 = gg * wpg; w2 < (gg + 1) * wpg; w2++) t += S.red[bb * MH_CWARPS + w2];
+                p.partials[((size_t)parity * PWGS_MAX_BATCH + lane) * cpc + rank] = t;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (dist) {                                                      // our share of batch g+1 must be in the ring
+                    const long long t0 = clock64();
+                    unsigned spins = 0;
+                    while (S.ctl[CTL_PROD_DONE] < g - 1)
+                        if ((++spins & 0xfff) == 0 && clock64() - t0 > MH_WATCHDOG_CYCLES) { atomicExch(p.abort_flag, 1); break; }
+                }
+                __threadfence_block();
+                red_release_add(p.counter, 1ull);
+            }
+        }
+        MH_PROF(1);
+
+        // ---------------- while the barrier is in flight: draw the next batch locally when the ring cannot provide it
+        const bool next_local = !dist || j <= 0;
+        if (next_local) mh_draw_local(p, S, e, cur ^ 1, n1_nb, n1_it, warp, lane);
+        MH_PROF(2);
+        if (tid == 0) {
+            const unsigned long long target = (unsigned long long)(g + 1) * (unsigned long long)cpc;
+            const long long t0 = clock64();
+            unsigned spins = 0;
+            while (ld_acquire(p.counter) < target)
+                if ((++spins & 0xff) == 0 && (*(volatile int *)p.abort_flag || clock64() - t0 > MH_WATCHDOG_CYCLES)) {
+                    atomicExch(p.abort_flag, 1);
+                    S.ctl[CTL_ABORT] = 1;
+                    break;
+                }
+        }
+        consumer_sync();
+        if (S.ctl[CTL_ABORT]) break;
+        MH_PROF(3);
+
+        // ---------------- every CTA sums the same partials in the same order -> bit-identical decisions everywhere;
+        // the loads of the next batch's ring slot (complete: every CTA posted its share before arriving) go out first so that
+        // all L2 round trips of this step overlap
+        const bool fetch = !next_local && n1_nb > 0;
+        const double *slot = p.ring + (size_t)((g + 1) % MH_RING) * (size_t)S.bufstride;
+        double f_pi = 0.0, f_phi = 0.0, f_h = 0.0, f_r = 0.0;
+        if (fetch) {
+            if (tid < n1_nb * KT) { f_pi = __ldcg(slot + tid); f_phi = __ldcg(slot + S.o_phi + tid); }
+            if (tid < n1_nb * T) f_h = __ldcg(slot + S.o_hast + tid);
+            if (tid < n1_nb) f_r = __ldcg(slot + S.o_logr + tid);
+        }
+        {
+            const double *pp = p.partials + (size_t)parity * PWGS_MAX_BATCH * cpc;
+            const int b0 = warp, b1 = warp + MH_CWARPS;                          // MAXB <= 2 * MH_CWARPS
+            double v0[5], v1[5];
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                const int r = lane + 32 * i;
+                v0[i] = (b0 < b_nb && r < cpc) ? __ldcg(pp + (size_t)b0 * cpc + r) : 0.0;
+                v1[i] = (b1 < b_nb && r < cpc) ? __ldcg(pp + (size_t)b1 * cpc + r) : 0.0;
+            }
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 5; i++) { t0 += v0[i]; t1 += v1[i]; }
+            for (int r = lane + 160; r < cpc; r += 32) {                         // chains wider than 160 CTAs (not on B200)
+                if (b0 < b_nb) t0 += __ldcg(pp + (size_t)b0 * cpc + r);
+                if (b1 < b_nb) t1 += __ldcg(pp + (size_t)b1 * cpc + r);
+            }
+            t0 = warp_sum(t0); t1 = warp_sum(t1);
+            if (lane == 0) { if (b0 < b_nb) S.llh[b0] = t0; if (b1 < b_nb) S.llh[b1] = t1; }
+        }
+        if (fetch) {
+            double *dst = S.prop_pi(cur ^ 1);
+            if (tid < n1_nb * KT) { dst[tid] = f_pi; dst[S.o_phi + tid] = f_phi; }
+            if (tid < n1_nb * T) dst[S.o_hast + tid] = f_h;
+            if (tid < n1_nb) dst[S.o_logr + tid] = f_r;
+            for (int i = tid + MH_CONSUMERS; i < n1_nb * KT; i += MH_CONSUMERS) { dst[i] = __ldcg(slot + i); dst[S.o_phi + i] = __ldcg(slot + S.o_phi + i); }
+            for (int i = tid + MH_CONSUMERS; i < n1_nb * T; i += MH_CONSUMERS) dst[S.o_hast + i] = __ldcg(slot + S.o_hast + i);
+        }
+        consumer_sync();
+        MH_PROF(4);
+
+        // ---------------- accept / reject (mh.cpp:73-100): lane b tests proposal b, the first accepted one wins
+        int sel = -1;
+        if (j < 0) {
+            cur_llh = S.llh[0];
+        } else {
+            bool ok = false;
+            if (lane < b_nb) {
+                double a = S.llh[lane] - cur_llh;
+                for (int tp = 0; tp < T; tp++) a += S.hast(cur)[lane * T + tp];
+                ok = S.logr(cur)[lane] < a;
+            }
+            const unsigned m = __ballot_sync(PWGS_FULL_MASK, ok);
+            sel = m ? __ffs(m) - 1 : -1;
+        }
+        pc[7]++;
+        g++;
+        MH_PROF(5);
+        if (sel < 0) {                                  // the batch drawn ahead is the real one
+            b_it = n1_it; b_nb = n1_nb; j++;
+            cur ^= 1;
+            continue;
+        }
+        // ---------------- update_params (mh.cpp:170-177) into the other state copy and redraw from the new state
+        cur_llh = S.llh[sel];
+        for (int i = tid; i < KT; i += MH_CONSUMERS) {
+            S.pi(e ^ 1)[i] = S.prop_pi(cur)[sel * KT + i];
+            S.phi(e ^ 1)[i] = S.prop_phi(cur)[sel * KT + i];
+        }
+        accepted++;
+        e ^= 1;
+        b_it += sel + 1;
+        // after an accept at position sel, expect the next one about as far away: batch = pow2 >= sel+1
+        b_nb = pow2_floor(min(min(MAXB, max(1, 2 * pow2_floor(sel + 1))), p.iters - b_it));
+        j = 0;
+        consumer_sync();
+        mh_refresh_state(p, S, e, tid, warp, lane);
+        consumer_sync();
+        mh_draw_local(p, S, e, cur ^ 1, b_nb, b_it, warp, lane);
+        cur ^= 1;
+        consumer_sync();
+        MH_PROF(6);
+    }
+    if (tid == 0) { __threadfence_block(); S.ctl[CTL_DONE] = 1; }
+    if (prof) for (int i = 0; i < 8; i++) p.prof[i] = pc[i];
+#undef MH_PROF
 
     if (rank == 0) {
-        for (int e = tid; e < KT; e += nthr) { p.pi_out[e] = cur_pi[e]; p.phi_out[e] = cur_phi[e]; }
+        for (int i = tid; i < KT; i += MH_CONSUMERS) { p.pi_out[i] = S.pi(e)[i]; p.phi_out[i] = S.phi(e)[i]; }
         if (tid == 0) { *p.acc_out = accepted; *p.llh_out = cur_llh + p.lbc_plain_sum; }
     }
 }

@@ -76,9 +76,11 @@ def test_bundled_golden_cases(oracle, gpu_lib):
             assert rel(eng.total_llh(gpu_lib.SEM_PY), oracle.total_llh(data, tree, oracle.SEM_PY)) < RTOL
 
 
-@pytest.mark.parametrize("batch", [1, 4, 8])
+@pytest.mark.parametrize("batch", [1, 4, 16])
 @pytest.mark.parametrize("ctas", [1, 3, 0])
-def test_mh_trajectory_matches_oracle(oracle, gpu_lib, batch, ctas):
+@pytest.mark.parametrize("stage", [1, 0])
+@pytest.mark.parametrize("dist", [-1, 1])
+def test_mh_trajectory_matches_oracle(oracle, gpu_lib, batch, ctas, stage, dist):
     """Same Philox stream => the kernel must walk the oracle's chain: equal accept count, equal final state."""
     data, tree = cases.synthetic_case(oracle, n_ssm=400, n_cnv=10, T=2, K=7, seed=21)   # random start: many early accepts
     iters, std, seed, stream = 300, 1000.0, 1234, 7
@@ -86,6 +88,8 @@ def test_mh_trajectory_matches_oracle(oracle, gpu_lib, batch, ctas):
     with cases.engine_for(gpu_lib, data, tree) as eng:
         eng.set_option("mh_batch", batch)
         eng.set_option("mh_ctas", ctas)
+        eng.set_option("mh_stage", stage)
+        eng.set_option("mh_dist", dist)      # 1: proposals two batches ahead come from the owner CTAs through the global ring
         got = eng.mh_run(iters, std, seed, stream)
     assert got["ratio"] * iters == want["accepted"]
     assert 0 < want["accepted"] < iters
