@@ -42,10 +42,14 @@ MH_STD = 100.0         # evolve.py:387
 METRIC = "mh_iterations_per_s"
 UNIT = "it/s"
 
-# FP64-pipe instruction model per likelihood term, counted from this repo's sm_100a SASS (DESIGN.md "Roofline"):
-FP64_PER_PLAIN_TERM = 66.0
-FP64_PER_CNV_TERM_BASE = 400.0
-FP64_PER_CNV_TERM_PER_NODE = 8.0
+# FP64-pipe instruction model of ONE proposal-likelihood pass, counted from this repo's sm_100a code (DESIGN.md "Roofline";
+# DFMA/DADD/DMUL/DSETP/DMNMX thread-instructions; conversions and MUFU run on other pipes):
+FP64_LOG = 26                     # pwgs_log_pos: 2 DADD + 4-step Newton reciprocal + 7 + polynomial 9 + tail 6
+FP64_PLAIN_TERM = 4 + 2 * FP64_LOG + 3                     # mu, 1-mu ; two logs ; a*log + (d-a)*log + accumulate   = 59
+FP64_CNV_STATE = 14 + 2 * FP64_LOG                         # nr+nv, mixture mean (division = 7), select, two logs, combine = 66
+FP64_CNV_PER_ENTRY = 2                                     # two DFMAs per sparse (node, state) entry
+FP64_LSE_EXTRA_STATE = 43                                  # running logsumexp: max, two exps (19 each), fma
+FP64_LSE_FINAL = FP64_LOG + 1                              # log of the sum (only when an SSM has more than one merged state)
 
 
 def workload(name):
@@ -57,12 +61,20 @@ def workload(name):
     raise SystemExit("unknown workload " + name)
 
 
-def algorithmic_work(s, K):
-    """Per MH iteration = ONE proposal-likelihood pass (current-state LLH cached): (bytes, fp64 instructions)."""
+def algorithmic_work(s, K, stats=None):
+    """Per MH iteration = ONE proposal-likelihood pass (current-state LLH cached): (bytes, fp64 instructions).
+    bytes: the records one pass streams; fp64: the instruction model above applied to the sparse CNV work list
+    (stats = counts of CNV-affected SSMs with 1/2/3 merged states and sum of entries x states, from the library)."""
     D, T = s["a"].shape
     M = int(np.count_nonzero(np.diff(s["cnv_ptr"]) > 0))
     by = (D - M) * (20 + 8 * T) + M * (12 + 8 * T + 8 * K)
-    fl = FP64_PER_PLAIN_TERM * (D - M) * T + (FP64_PER_CNV_TERM_PER_NODE * K + FP64_PER_CNV_TERM_BASE) * M * T
+    if stats is None:
+        fl = None
+    else:
+        n1, n2, n3, es = stats
+        cnv = FP64_CNV_STATE * (n1 + 2 * n2 + 3 * n3) + FP64_CNV_PER_ENTRY * es + FP64_LSE_EXTRA_STATE * (n2 + 2 * n3) \
+            + FP64_LSE_FINAL * (n2 + n3) + M
+        fl = float(T * (FP64_PLAIN_TERM * (D - M) + cnv))
     return by, fl, D, M, T
 
 
@@ -188,7 +200,7 @@ def main():
 
     s, wl_desc = workload(args.workload)
     K = len(s["parent"])
-    by_it, fp_it, D, M, T = algorithmic_work(s, K)
+    by_it, _, D, M, T = algorithmic_work(s, K)
     config = {"workload": wl_desc, "n_ssm": int(s["n_ssm"]), "n_cnv": int(D - s["n_ssm"]), "n_cnv_affected_ssm": M, "ntps": T,
               "tree_nodes": K, "mh_iterations_per_step": MH_ITR, "mh_std": mh_std, "chains": n_gpus, "parallelism": "1 chain per GPU, no collective"}
 
@@ -245,11 +257,15 @@ def main():
         eng.set_option("mh_batch", args.mh_batch)
     if args.profile_phases:
         eng.set_option("mh_profile", 1)
+    stats = [eng.get_option(n) for n in ("cnv_nu1", "cnv_nu2", "cnv_nu3", "cnv_entry_states")]
+    by_it, fp_it, D, M, T = algorithmic_work(s, K, stats)
     ext = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     seed = 20261019
 
     for w in range(args.warmup):
+        with torch.cuda.stream(ext):
+            flush.zero_()                                                   # also loads torch's fill kernel before the timed region
         eng.mh_launch(MH_ITR, mh_std, seed, 1000 * rank + w)
         eng.mh_wait(fetch=False)
     fp64_peak = P.fp64_peak(local_rank)                                 # DFMA thread-instr/s, measured on this GPU now
@@ -264,16 +280,22 @@ def main():
         sampler.start()
     with torch.cuda.stream(ext):
         e0.record(ext)
+        step_wall = []
         for k in range(args.steps):
+            tw0 = time.perf_counter()
             flush.zero_()                                               # L2 flush between timed steps (inside the bracket)
             eng.mh_launch(MH_ITR, mh_std, seed, 1000 * rank + 100 + k)
             r = eng.mh_wait(fetch=False)
             kernel_ms.append(r["kernel_ms"])
             ratios.append(r["ratio"])
+            step_wall.append(1e3 * (time.perf_counter() - tw0))
         e1.record(ext)
     barrier()
     clocks = sampler.stop() if sampler else None
     total_ms = max_over_ranks(e0.elapsed_time(e1))
+    if rank == 0:
+        print("value loop: events %.2f ms total; host wall per step: mean %.2f max %.2f ms; kernel per step: mean %.2f max %.2f ms"
+              % (total_ms, statistics.mean(step_wall), max(step_wall), statistics.mean(kernel_ms), max(kernel_ms)), file=sys.stderr)
     launches = eng.get_option("launches") - launches0
     value = n_gpus * args.steps * MH_ITR / (total_ms * 1e-3)
     kms = statistics.mean(kernel_ms)
@@ -317,6 +339,7 @@ def main():
                 "frac": fp_it * its_kernel / fp64_peak, "traffic": None,
                 "peak_source": "pwgs_fp64_peak: DFMA chains measured live on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
                 "algorithmic_fp64_instr_per_iteration": fp_it, "kernel_ms_per_launch": kms,
+                "cnv_ssm_by_merged_states": stats[:3], "cnv_entry_states": stats[3],
                 "hbm": {"achieved": by_it * its_kernel / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": by_it * its_kernel / 1e9 / hbm_peak,
                         "algorithmic_bytes_per_iteration": by_it,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}}

@@ -149,6 +149,9 @@ int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
     const int D = n_ssm + n_cnv, T = ntps;
     for (size_t i = 0; i < (size_t)D * T; i++)
         if (a[i] < 0 || d[i] < a[i]) return fail(PWGS_EINVAL, "need 0 <= a <= d for every datum and sample (index " + std::to_string(i) + ")");
+    for (int j = 0; j < D; j++)
+        if (!(mu_r[j] > 0.0 && mu_r[j] < 1.0 && mu_v[j] > 0.0 && mu_v[j] < 1.0))
+            return fail(PWGS_EINVAL, "mu_r and mu_v must lie strictly inside (0,1) (datum " + std::to_string(j) + ")");
     int L = 0;
     if (cnv_ptr) {
         if (cnv_ptr[0] != 0) return fail(PWGS_EINVAL, "cnv_ptr[0] must be 0");
@@ -277,6 +280,9 @@ int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node
         int dd = depth[v];
         for (int i = (int)path.size() - 1; i >= 0; i--) depth[path[i]] = ++dd;
     }
+    for (size_t i = 0; i < (size_t)K * c->T; i++)
+        if (!(phi[i] >= 0.0 && phi[i] <= 1.000001 && pi[i] >= 0.0 && pi[i] <= 1.000001))
+            return fail(PWGS_EINVAL, "phi and pi must lie in [0,1] (node " + std::to_string(i / c->T) + ")");
     for (int j = 0; j < c->D; j++)
         if (node_of_datum[j] < 0 || node_of_datum[j] >= K) return fail(PWGS_EINVAL, "node_of_datum out of range at datum " + std::to_string(j));
     // ---- Euler tour (children in increasing index) and the children-first accumulation order
@@ -405,18 +411,19 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     CUDA_TRY(cudaMemcpyAsync(c->plist.p, &p, sizeof(p), cudaMemcpyHostToDevice, c->stream));
 
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    cudaError_t e = cudaFuncSetAttribute(mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const void *kfn = stage ? (const void *)mh_kernel<true> : (const void *)mh_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
         const MhParams *plist = c->plist.p;
         void *args[] = {(void *)&plist, (void *)&cpc};
-        e = cudaLaunchCooperativeKernel((void *)mh_kernel, dim3(cpc), dim3(MH_THREADS), args, smem, c->stream);
+        e = cudaLaunchCooperativeKernel(kfn, dim3(cpc), dim3(MH_THREADS), args, smem, c->stream);
     }
     if (e != cudaSuccess) {
         cudaFuncAttributes fa;
         int occ = -1;
         cudaGetLastError();
-        cudaFuncGetAttributes(&fa, mh_kernel);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_kernel, MH_THREADS, smem);
+        cudaFuncGetAttributes(&fa, kfn);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_kernel<true>, MH_THREADS, smem);
         return fail(PWGS_ECUDA, std::string("mh_kernel launch: ") + cudaGetErrorString(e) + " (grid " + std::to_string(cpc) + " x " +
                     std::to_string(MH_THREADS) + " threads, " + std::to_string(smem) + " B dynamic smem, " + std::to_string(fa.numRegs) +
                     " regs, maxThreadsPerBlock " + std::to_string(fa.maxThreadsPerBlock) + ", static smem " + std::to_string(fa.sharedSizeBytes) +
@@ -564,10 +571,39 @@ int pwgs_set_option(pwgs_ctx *c, const char *name, int64_t value)
     return PWGS_OK;
 }
 
+// Work statistics of the sparse CNV list (for the roofline model): number of CNV-affected SSMs with 1 / 2 / 3 merged states
+// and sum over SSMs of entries x states.
+static int cnv_work_stats(pwgs_ctx *c, int64_t out[4])
+{
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called first");
+    if (c->M == 0) return PWGS_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int cpc = c->opt_ctas > 0 ? std::min(c->opt_ctas, c->n_sms) : c->n_sms;
+    int rc = prepare_cnv_work(c, cpc);
+    if (rc != PWGS_OK) return rc;
+    std::vector<int> code(c->M);
+    CUDA_TRY(cudaMemcpyAsync(code.data(), c->code_tmp.p, sizeof(int) * c->M, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int m = 0; m < c->M; m++) {
+        int ne = code[m] & 0xff, nu = (code[m] >> 8) & 3;
+        if (nu >= 1 && nu <= 3) out[nu - 1]++;
+        out[3] += (int64_t)ne * nu;
+    }
+    return PWGS_OK;
+}
+
 int pwgs_get_option(pwgs_ctx *c, const char *name, int64_t *value)
 {
     if (!c || !name || !value) return fail(PWGS_EINVAL, "NULL argument");
     std::string n(name);
+    if (n == "cnv_nu1" || n == "cnv_nu2" || n == "cnv_nu3" || n == "cnv_entry_states") {
+        int64_t st[4];
+        int rc = cnv_work_stats(c, st);
+        if (rc != PWGS_OK) return rc;
+        *value = st[n == "cnv_nu1" ? 0 : n == "cnv_nu2" ? 1 : n == "cnv_nu3" ? 2 : 3];
+        return PWGS_OK;
+    }
     if (n == "mh_batch") *value = c->opt_batch;
     else if (n == "mh_ctas") *value = c->opt_ctas;
     else if (n == "n_sms") *value = c->n_sms;

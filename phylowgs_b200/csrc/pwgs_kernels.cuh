@@ -6,6 +6,7 @@
 // Citations are file:line relative to the reference checkout.
 #pragma once
 #include "pwgs_device.cuh"
+#include <type_traits>
 
 // ============================================================================ K0
 __global__ void lbc_kernel(int n, const int *__restrict__ a, const int *__restrict__ d, double *__restrict__ out)
@@ -685,7 +686,7 @@ __device__ __noinline__ void mh_producer(const MhParams &p, const MhSmem &S, int
     int job = 1;                                                                // jobs are numbered by global batch, from 1
 #pragma unroll 1
     for (;;) {
-        while (S.ctl[CTL_GEN] < job && !S.ctl[CTL_DONE]) { }
+        while (S.ctl[CTL_GEN] < job && !S.ctl[CTL_DONE]) __nanosleep(256);    // idle most of the time: stay out of the issue slots
         if (S.ctl[CTL_GEN] < job) return;                                        // done and nothing new posted
         __threadfence_block();
         const volatile int *jb = S.ctl + CTL_JOB + 3 * (job & 1);
@@ -726,6 +727,7 @@ __device__ __noinline__ void mh_producer(const MhParams &p, const MhSmem &S, int
 // the first one's barrier is in flight); from the third on, each (proposal, sample) is drawn ONCE per chain by the producer
 // warp of its owner CTA two batches ahead and travels through a ring in global memory under the chain barrier's release /
 // acquire.  Chains with few CTAs keep drawing locally.
+template <bool STAGED>
 __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, int cpc)
 {
     double *sm = mh_sm;
@@ -761,9 +763,8 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
     const int pchunk = (p.Dp + cpc - 1) / cpc, p0 = min(p.Dp, rank * pchunk), p1 = min(p.Dp, p0 + pchunk);
     const CnvWork &cw = p.cw;
     const int cbase = rank * cw.cchunk, np = p1 - p0, nc = (p.M - rank + cpc - 1) / cpc;
-    SliceShared ss;
-    SliceGlobal sg;
-    if (p.stage) {
+    typename std::conditional<STAGED, SliceShared, SliceGlobal>::type sl;
+    if constexpr (STAGED) {
         // carve the staging area behind the node tables (16-byte aligned) and copy the slice once
         char *q = (char *)(S.tout + K);
         q = (char *)mh_align16((size_t)q);
@@ -794,14 +795,14 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
                 s_ecoef[(size_t)e * cc + i] = cw.ecoef[(size_t)e * cw.Mp + cbase + i];
             }
         }
-        ss.np = np; ss.pstride = pchunk; ss.nc = nc; ss.cstride = cc; ss.T = T;
-        ss.o_ecoef = (int)(((char *)s_ecoef - (char *)sm) / 16); ss.o_pdbl = (int)(s_pmu - sm); ss.o_cdbl = (int)(s_cd - sm);
-        ss.o_pint = (int)(s_pi - (int *)sm); ss.o_cint = (int)(s_ci - (int *)sm);
+        sl.np = np; sl.pstride = pchunk; sl.nc = nc; sl.cstride = cc; sl.T = T;
+        sl.o_ecoef = (int)(((char *)s_ecoef - (char *)sm) / 16); sl.o_pdbl = (int)(s_pmu - sm); sl.o_cdbl = (int)(s_cd - sm);
+        sl.o_pint = (int)(s_pi - (int *)sm); sl.o_cint = (int)(s_ci - (int *)sm);
     } else {
-        sg.np = np; sg.pstride = p.Dp; sg.nc = nc; sg.cstride = cw.Mp;
-        sg.g_pmu_r = p.pmu_r + p0; sg.g_pmu_v = p.pmu_v + p0; sg.g_pnode = p.pnode + p0; sg.g_pa = p.pa + p0; sg.g_pd = p.pd + p0;
-        sg.g_cmu_r = cw.mu_r + cbase; sg.g_clbc = cw.lbc + cbase; sg.g_ccode = cw.code + cbase; sg.g_ca = cw.a + cbase;
-        sg.g_cd = cw.d + cbase; sg.g_cenode = cw.enode + cbase; sg.g_cecoef = cw.ecoef + cbase;
+        sl.np = np; sl.pstride = p.Dp; sl.nc = nc; sl.cstride = cw.Mp;
+        sl.g_pmu_r = p.pmu_r + p0; sl.g_pmu_v = p.pmu_v + p0; sl.g_pnode = p.pnode + p0; sl.g_pa = p.pa + p0; sl.g_pd = p.pd + p0;
+        sl.g_cmu_r = cw.mu_r + cbase; sl.g_clbc = cw.lbc + cbase; sl.g_ccode = cw.code + cbase; sl.g_ca = cw.a + cbase;
+        sl.g_cd = cw.d + cbase; sl.g_cenode = cw.enode + cbase; sl.g_cecoef = cw.ecoef + cbase;
     }
     __syncthreads();
 
@@ -842,11 +843,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
 
         // ---------------- likelihood (param_post) of the CTA's slice for every proposal of the batch
         const int bu = b_nb >= MH_BU ? MH_BU : 1;      // thread groups of MH_BU proposals, or one proposal per group
-        if (p.stage) {
-            if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, ss, cur, b_nb, warp, lane); else mh_likelihood<1>(p, S, ss, cur, b_nb, warp, lane);
-        } else {
-            if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sg, cur, b_nb, warp, lane); else mh_likelihood<1>(p, S, sg, cur, b_nb, warp, lane);
-        }
+        if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, b_nb, warp, lane); else mh_likelihood<1>(p, S, sl, cur, b_nb, warp, lane);
         consumer_sync();
         MH_PROF(0);
 
