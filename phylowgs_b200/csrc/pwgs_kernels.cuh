@@ -588,8 +588,29 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
                 double nr[BU], nv[BU];
 #pragma unroll
                 for (int bb = 0; bb < BU; bb++) nr[bb] = nv[bb] = 0.0;
+                // the first four entries are loaded up front (predicated) so their shared-memory latencies overlap; SSMs with
+                // more entries (three or more CNV links) finish in the loop below
+                {
+                    int nd[4], cu[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const bool v = e < ne;
+                        nd[e] = v ? sl.cenode(e, idx) * T + tp : 0;
+                        cu[e] = v ? sl.cecoef(e, idx, u) : 0;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const double dr = (double)(short)(cu[e] & 0xffff), dv = (double)(cu[e] >> 16);
+#pragma unroll
+                        for (int bb = 0; bb < BU; bb++) {
+                            const double ph = bphi[bb * KT + nd[e]];
+                            nr[bb] = fma(ph, dr, nr[bb]);
+                            nv[bb] = fma(ph, dv, nv[bb]);
+                        }
+                    }
+                }
 #pragma unroll 1
-                for (int e = 0; e < ne; e++) {
+                for (int e = 4; e < ne; e++) {
                     const int node = sl.cenode(e, idx) * T + tp;
                     const int cu = sl.cecoef(e, idx, u);
                     const double dr = (double)(short)(cu & 0xffff), dv = (double)(cu >> 16);

@@ -1,0 +1,101 @@
+"""The chain's compute backend: flattens the host tree into the arrays of the C ABI and forwards every likelihood / MH request
+to the device context (phylowgs_b200.engine.Engine over libpwgs_b200.so).  This replaces the reference's file round trip
+(params.write_tree / write_data_state -> mh.o -> c_params.txt, params.py:30-194).  There is no CPU implementation here."""
+import numpy as np
+
+from .. import SEM_PY
+from ..engine import Engine
+
+
+def arrays_from_data(data):
+    """Datum list (SSMs s0.. then CNVs c0.., util2.py:53-94 order) -> the arrays of pwgs_create."""
+    n_ssm = sum(1 for d in data if d.id[0] == "s")
+    for i, d in enumerate(data):
+        want = ("s%d" % i) if i < n_ssm else ("c%d" % (i - n_ssm))
+        if d.id != want:
+            raise ValueError("data must be ordered s0,s1,...,c0,c1,... (README.md:23-25); found %r at position %d" % (d.id, i))
+        d.index = i
+    a = np.array([d.a for d in data], dtype=np.int32)
+    dd = np.array([d.d for d in data], dtype=np.int32)
+    mu_r = np.array([d.mu_r for d in data], dtype=np.float64)
+    mu_v = np.array([d.mu_v for d in data], dtype=np.float64)
+    ptr = np.zeros(n_ssm + 1, dtype=np.int32)
+    idx, c1, c2 = [], [], []
+    for j in range(n_ssm):
+        for cnv, x, y in data[j].cnv:
+            idx.append(cnv.index - n_ssm)
+            c1.append(x)
+            c2.append(y)
+        ptr[j + 1] = len(idx)
+    return dict(a=a, d=dd, mu_r=mu_r, mu_v=mu_v, n_ssm=n_ssm, cnv_ptr=ptr, cnv_idx=np.array(idx, dtype=np.int32),
+                cnv_c1=np.array(c1, dtype=np.int32), cnv_c2=np.array(c2, dtype=np.int32))
+
+
+def flatten_tree(tssb):
+    """Preorder node list (get_mixture order = the ids evolve.py:175-177 assigns) -> (nodes, parent, node_of_datum, phi, pi)."""
+    _, nodes = tssb.get_mixture()
+    pos = {id(nd): k for k, nd in enumerate(nodes)}
+    parent = np.array([-1 if nd.parent() is None else pos[id(nd.parent())] for nd in nodes], dtype=np.int32)
+    nod = np.zeros(tssb.num_data, dtype=np.int32)
+    for k, nd in enumerate(nodes):
+        if nd.data:
+            nod[list(nd.data)] = k
+    phi = np.array([np.asarray(nd.params, dtype=np.float64).reshape(-1) for nd in nodes])
+    pi = np.array([np.asarray(nd.pi, dtype=np.float64).reshape(-1) for nd in nodes])
+    return nodes, parent, nod, phi, pi
+
+
+class Backend(object):
+    """Interface the host samplers use.  `GpuBackend` is the product; the parity tests plug the CPU oracle in behind the same
+    interface (tests/oracle_backend.py) to obtain the chain the GPU chain must reproduce."""
+
+    n_ssm = 0
+
+    def set_tree_arrays(self, parent, node_of_datum, phi, pi):
+        raise NotImplementedError
+
+    def llh_rows(self, rows):
+        raise NotImplementedError
+
+    def total_llh(self):
+        raise NotImplementedError
+
+    def mh(self, iters, std, seed, stream):
+        raise NotImplementedError
+
+    # -- shared glue
+    def sync_tree(self, tssb):
+        nodes, parent, nod, phi, pi = flatten_tree(tssb)
+        self.set_tree_arrays(parent, nod, phi, pi)
+        self.nodes = nodes
+        return nodes
+
+    def datum_llh(self, tssb, datum, node):
+        """Single (datum, node) query behind alleles.logprob (alleles.py:52-53); the samplers use the batched grid instead."""
+        nodes = self.sync_tree(tssb)
+        k = next(i for i, nd in enumerate(nodes) if nd is node)
+        return float(self.llh_rows(np.array([datum.index], dtype=np.int32))[0, k])
+
+
+class GpuBackend(Backend):
+    def __init__(self, data, device=0):
+        arr = arrays_from_data(data)
+        self.n_ssm = arr["n_ssm"]
+        self.n_cnv = len(data) - self.n_ssm
+        self.ntps = arr["a"].shape[1]
+        self.engine = Engine(device=device, **arr)
+
+    def set_tree_arrays(self, parent, node_of_datum, phi, pi):
+        self.engine.set_tree(parent, node_of_datum, phi, pi)
+
+    def llh_rows(self, rows):
+        return self.engine.llh_rows(rows, SEM_PY)
+
+    def total_llh(self):
+        return self.engine.total_llh(SEM_PY)
+
+    def mh(self, iters, std, seed, stream):
+        return self.engine.mh_run(iters, std, seed, stream)
+
+    def close(self):
+        self.engine.close()

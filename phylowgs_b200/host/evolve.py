@@ -1,0 +1,457 @@
+"""Single-chain driver with the reference's CLI, files and status lines (evolve.py:31-497), Python 3, device-backed.
+
+    python -m phylowgs_b200.host.evolve [-O DIR] [-B 1000] [-s 2500] [-i 5000] [-r SEED] [-b 100] [-S 10] [-t TMP] [-p params.json] ssm cnv
+
+Writes trees.zip (members burnin_<i>_<llh> / tree_<i>_<llh> = protocol-2 pickles of the TSSB, util2.py:250-262),
+mcmc_samples.txt, random_seed.txt, state.initial.pickle / state.last.pickle (+ .backup copies) exactly where the reference
+does; resumes from state.last.pickle when it exists (CLI then ignored except -O, evolve.py:347-349); exit codes 0 / 1 / 3.
+The device is chosen with PWGS_DEVICE (default 0) so the CLI surface is unchanged.
+"""
+import argparse
+import csv
+import json
+import os
+import pickle
+import shutil
+import signal
+import sys
+import tempfile
+import threading
+import time
+import traceback
+import zipfile
+from collections import OrderedDict
+from datetime import datetime
+
+import numpy as np
+
+from . import model
+from .backend import GpuBackend
+from .model import TSSB, Datum, alleles, boundbeta
+from .params import get_c_fnames, metropolis
+
+csv.field_size_limit(2147483647)        # .cnv rows can list thousands of SSMs (util2.py:13-18)
+
+
+def logmsg(msg, fd=None):
+    fd = fd or sys.stdout
+    fd.write("[%s] %s\n" % (datetime.now(), msg))
+    fd.flush()
+
+
+# ------------------------------------------------------------------ inputs (util2.py:40-94)
+def parse_physical_cnvs(text):
+    out = []
+    for item in text.split(";"):
+        cnv = dict(f.split("=", 1) for f in item.split(","))
+        for key in ("start", "end", "major_cn", "minor_cn"):
+            cnv[key] = int(cnv[key])
+        cnv["cell_prev"] = [float(c) for c in cnv["cell_prev"].split("|")]
+        out.append(cnv)
+    return out
+
+
+def load_data(ssm_fn, cnv_fn):
+    """-> (data in file order: SSMs then CNVs, n_ssms, n_cnvs, cnv_logical_physical_mapping).  The reference returns the data in
+    Python-2 dict order of the ids (util2.py:94); file order is what mh.cpp indexes by (params.py:71-76) and what we use."""
+    by_id = OrderedDict()
+    with open(ssm_fn, newline="") as f:
+        for row in csv.DictReader(f, delimiter="\t"):
+            mu_r = float(row["mu_r"]) if "mu_r" in row else 0.0
+            mu_v = float(row["mu_v"]) if "mu_v" in row else 0.0
+            by_id[row["id"]] = Datum(row["gene"], row["id"], [int(x) for x in row["a"].split(",")],
+                                     [int(x) for x in row["d"].split(",")], mu_r, mu_v)
+    n_ssms = len(by_id)
+    mapping = {}
+    with open(cnv_fn, newline="") as f:
+        for row in csv.DictReader(f, delimiter="\t"):
+            cid = row["cnv"]
+            mapping[cid] = parse_physical_cnvs(row["physical_cnvs"])
+            cnv = Datum(cid, cid, [int(x) for x in row["a"].split(",")], [int(x) for x in row["d"].split(",")], 0.999, 0.5)
+            by_id[cid] = cnv
+            for tok in filter(None, (row.get("ssms") or "").split(";")):
+                sid, c1, c2 = tok.split(",")
+                by_id[sid].cnv.append((cnv, int(c1), int(c2)))
+    data = list(by_id.values())
+    for i, d in enumerate(data):
+        d.index = i
+    return data, n_ssms, len(data) - n_ssms, mapping
+
+
+# ------------------------------------------------------------------ tree metadata (util2.py:99-115)
+def set_node_height(tssb):
+    stack = [(tssb.root["node"], 0)]
+    while stack:
+        nd, ht = stack.pop()
+        nd.ht = ht
+        stack.extend((c, ht + 1) for c in nd.children())
+
+
+def set_path_from_root_to_node(tssb):
+    for nd in tssb.get_nodes():
+        nd.path = nd.get_ancestors()
+
+
+def map_datum_to_node(tssb):
+    for nd in tssb.get_nodes():
+        for n in nd.data:
+            tssb.data[n].node = nd
+
+
+# ------------------------------------------------------------------ persistence (util2.py:157-262)
+def install_pickle_aliases():
+    """Pickle the model classes under the module names the reference's readers expect (tssb.TSSB, alleles.alleles, node.Node,
+    data.Datum) and let this process unpickle them again."""
+    import types
+    for cls in (TSSB, alleles, model.Node, Datum):
+        name = model.PICKLE_MODULES[cls.__name__]
+        cls.__module__ = name
+        mod = sys.modules.get(name)
+        if mod is None:
+            mod = types.ModuleType(name)
+            sys.modules[name] = mod
+        setattr(mod, cls.__name__, cls)
+
+
+def rm_safely(fn):
+    try:
+        os.remove(fn)
+    except FileNotFoundError:
+        pass
+
+
+class BackupManager(object):
+    def __init__(self, filenames):
+        self._pairs = [(fn, os.path.realpath(fn) + ".backup") for fn in filenames]
+
+    def save_backup(self):
+        for fn, bak in self._pairs:
+            shutil.copy2(fn, bak)
+
+    def restore_backup(self):
+        for fn, bak in self._pairs:
+            shutil.copy2(bak, fn)
+
+    def remove_backup(self):
+        for _, bak in self._pairs:
+            rm_safely(bak)
+
+
+class StateManager(object):
+    default_last_state_fn = "state.last.pickle"
+    default_initial_state_fn = "state.initial.pickle"
+
+    def _dump(self, state, fn):
+        with open(fn, "wb") as f:
+            pickle.dump(state, f, protocol=2)
+
+    def write_state(self, state):
+        self._dump(state, self.default_last_state_fn)
+
+    def write_initial_state(self, state):
+        self._dump(state, self.default_initial_state_fn)
+
+    def load_state(self):
+        with open(self.default_last_state_fn, "rb") as f:
+            return pickle.load(f)
+
+    def state_exists(self):
+        return os.path.isfile(self.default_last_state_fn)
+
+
+class CorruptZipFileError(Exception):
+    pass
+
+
+class TreeWriter(object):
+    default_archive_fn = "trees.zip"
+
+    def __init__(self, resume_run=False):
+        if resume_run:
+            with zipfile.ZipFile(self.default_archive_fn) as z:
+                if z.testzip() is not None:
+                    raise CorruptZipFileError("Corrupt zip file: %s" % self.default_archive_fn)
+        else:
+            rm_safely(self.default_archive_fn)
+
+    def _open(self):
+        return zipfile.ZipFile(self.default_archive_fn, "a", compression=zipfile.ZIP_DEFLATED, allowZip64=True)
+
+    def add_extra_file(self, filename, data):
+        with self._open() as z:
+            z.writestr(filename, data)
+
+    def write_trees(self, serialized_trees):
+        with self._open() as z:
+            for blob, idx, llh in serialized_trees:
+                z.writestr("%s_%s_%s" % ("burnin" if idx < 0 else "tree", idx, llh), blob)
+
+
+# ------------------------------------------------------------------ the chain
+def _attach(state, codes):
+    """(Re)create the process-local parts of a chain: its generator and its device context."""
+    tssb = state["tssb"]
+    tssb.rng = np.random.RandomState()
+    tssb.backend = GpuBackend(codes, device=int(os.environ.get("PWGS_DEVICE", "0")))
+    tssb.data = codes
+    for d in codes:
+        d.tssb = tssb
+    return tssb
+
+
+def start_new_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config, ssm_file, cnv_file, params_file,
+                  burnin_samples, num_samples, mh_itr, mh_std, write_state_every, write_backups_every, rand_seed, tmp_dir):
+    state = {}
+    if rand_seed is not None:
+        state["rand_seed"] = int(rand_seed)
+    else:                                       # CLI -> random_seed.txt -> fresh seed (evolve.py:33-53)
+        try:
+            with open("random_seed.txt") as f:
+                state["rand_seed"] = int(f.read().strip())
+        except (OSError, ValueError):
+            state["rand_seed"] = int(np.random.randint(2 ** 32, dtype=np.uint64))
+    with open("random_seed.txt", "w") as f:
+        f.write("%s\n" % state["rand_seed"])
+    state.update(working_dir=os.getcwd(), ssm_file=ssm_file, cnv_file=cnv_file, tmp_dir=tmp_dir,
+                 write_state_every=write_state_every, write_backups_every=write_backups_every)
+
+    codes, n_ssms, n_cnvs, mapping = load_data(ssm_file, cnv_file)
+    if not codes:
+        logmsg("No SSMs or CNVs provided. Exiting.", sys.stderr)
+        return
+    ntps = len(codes[0].a)
+    state["glist"] = [d.name for d in codes if len(d.name) > 0]
+    state.update(burnin=burnin_samples, num_samples=num_samples, dp_alpha=25.0, dp_gamma=1.0, alpha_decay=0.25,
+                 mh_burnin=0, mh_itr=mh_itr, mh_std=mh_std)
+    state["cd_llh_traces"] = np.zeros((num_samples, 1))
+    state["burnin_cd_llh_traces"] = np.zeros((burnin_samples, 1))
+
+    rng = np.random.RandomState(state["rand_seed"])
+    backend = GpuBackend(codes, device=int(os.environ.get("PWGS_DEVICE", "0")))
+    root = alleles(conc=0.1, ntps=ntps)
+    tssb = TSSB(dp_alpha=state["dp_alpha"], dp_gamma=state["dp_gamma"], alpha_decay=state["alpha_decay"], root_node=root,
+                data=codes, rng=rng, backend=backend)
+    # one child under the (empty) root takes all the data (evolve.py:84-98)
+    tssb.root["sticks"] = np.vstack([tssb.root["sticks"], .999999])
+    child = root.spawn()
+    tssb.root["children"].append({"node": child, "main": boundbeta(rng, 1.0, tssb.alpha_decay * tssb.dp_alpha),
+                                  "sticks": np.empty((0, 1)), "children": []})
+    for n in range(tssb.num_data):
+        root.remove_datum(n)
+        child.add_datum(n)
+        tssb.assignments[n] = child
+    for d in codes:
+        d.tssb = tssb
+    state["tssb"] = tssb
+
+    writer = TreeWriter()
+    writer.add_extra_file("cnv_logical_physical_mapping.json", json.dumps(mapping))
+    params = {}
+    if params_file is not None:
+        with open(params_file) as f:
+            params = json.load(f)
+    writer.add_extra_file("params.json", json.dumps(params))
+
+    state_manager.write_initial_state(state)
+    logmsg("Starting MCMC run...")
+    state["last_iteration"] = -state["burnin"] - 1
+    with open("mcmc_samples.txt", "w") as f:
+        f.write("Iteration\tLLH\tTime\n")
+    do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, state, writer, codes, n_ssms, n_cnvs, ntps, tmp_dir)
+
+
+def resume_existing_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config):
+    try:
+        state = state_manager.load_state()
+        os.chdir(state["working_dir"])
+        writer = TreeWriter(resume_run=True)
+    except Exception:
+        logmsg("Restoring state failed:", sys.stderr)
+        traceback.print_exc()
+        logmsg("Restoring from backup and trying again.", sys.stderr)
+        backup_manager.restore_backup()
+        state = state_manager.load_state()
+        os.chdir(state["working_dir"])
+        writer = TreeWriter(resume_run=True)
+    tssb = state["tssb"]
+    codes = tssb.data                           # the pickled data carry the assignments' bookkeeping (datum.node)
+    n_ssms = sum(1 for d in codes if d.id[0] == "s")
+    _attach(state, codes)
+    tssb.rng.set_state(state["rand_state"])
+    do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, state, writer, codes, n_ssms, len(codes) - n_ssms,
+            len(codes[0].a), state["tmp_dir"])
+
+
+def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, state, tree_writer, codes, n_ssms, n_cnvs, ntps,
+            tmp_dir_parent):
+    start_iter = state["last_iteration"] + 1
+    unwritten, sample_times = [], []
+    t_last = time.time()
+    config["tmp_dir"] = tempfile.mkdtemp(prefix="pwgsdataexchange.", dir=tmp_dir_parent)
+    tssb = state["tssb"]
+
+    for iteration in range(start_iter, state["num_samples"]):
+        sys.stdout.flush()
+        safe_to_exit.set()
+        status = OrderedDict(iteration=iteration, trees_sampled=state["burnin"] + iteration,
+                             total_trees=state["burnin"] + state["num_samples"])
+
+        tssb.resample_assignments()
+        tssb.cull_tree()
+        _, nodes = tssb.get_mixture()
+        for i, nd in enumerate(nodes):
+            nd.id = i
+        set_node_height(tssb)
+        set_path_from_root_to_node(tssb)
+        map_datum_to_node(tssb)
+
+        state["mh_acc"] = metropolis(tssb, state["mh_itr"], state["mh_std"], state["mh_burnin"], n_ssms, n_cnvs, state["ssm_file"],
+                                     state["cnv_file"], state["rand_seed"], ntps, config["tmp_dir"],
+                                     stream=iteration + state["burnin"])
+        acc = float(state["mh_acc"])
+        if acc < 0.08 and state["mh_std"] < 10000:
+            state["mh_std"] = state["mh_std"] * 2.0
+            logmsg("Shrinking MH proposals. Now %f" % state["mh_std"])
+        if 0.5 < acc < 0.99:
+            state["mh_std"] = state["mh_std"] / 2.0
+            logmsg("Growing MH proposals. Now %f" % state["mh_std"])
+
+        tssb.resample_sticks()
+        tssb.resample_stick_orders()
+        tssb.resample_hypers(dp_alpha=True, alpha_decay=True, dp_gamma=True)
+
+        last_llh = tssb.complete_data_log_likelihood()
+        status["llh"] = last_llh
+        if iteration >= 0:
+            state["cd_llh_traces"][iteration] = last_llh
+            status["nodes"] = len(tssb.get_nodes())
+            status["mh_acc"] = state["mh_acc"]
+            status["dp_alpha"] = tssb.dp_alpha
+            status["dp_gamma"] = tssb.dp_gamma
+            status["alpha_decay"] = tssb.alpha_decay
+        else:
+            state["burnin_cd_llh_traces"][iteration + state["burnin"]] = last_llh
+        logmsg(" ".join("%s=%s" % kv for kv in status.items()))
+
+        unwritten.append((pickle.dumps(tssb, protocol=2), iteration, last_llh))
+        state["rand_state"] = tssb.rng.get_state()
+        state["last_iteration"] = iteration
+        if len([c for c in tssb.root["children"] if c["node"].has_data()]) > 1:
+            logmsg("Polyclonal tree detected with %s clones." % len(tssb.root["children"]))
+
+        now = time.time()
+        sample_times.append(now - t_last)
+        t_last = now
+
+        safe_to_exit.clear()                    # no exit in the middle of a zip / pickle write (evolve.py:247-250)
+        write_backup = iteration % state["write_backups_every"] == 0 and iteration != start_iter
+        write_state = iteration % state["write_state_every"] == 0
+        if write_backup or write_state or iteration == state["num_samples"] - 1:
+            with open("mcmc_samples.txt", "a") as f:
+                f.write("\n".join("%s\t%s\t%s" % (it, llh, dt) for (_, it, llh), dt in zip(unwritten, sample_times)) + "\n")
+            tree_writer.write_trees(unwritten)
+            state_manager.write_state(state)
+            unwritten, sample_times = [], []
+            if write_backup:
+                backup_manager.save_backup()
+
+    backup_manager.remove_backup()
+    safe_to_exit.set()
+    run_succeeded.set()
+
+
+# ------------------------------------------------------------------ CLI (evolve.py:287-497)
+def create_argparser(full=True):
+    p = argparse.ArgumentParser(description="Run PhyloWGS to infer subclonal composition from SSMs and CNVs",
+                                formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument("-O", "--output-dir", dest="output_dir", help="Path to output directory")
+    if full:
+        p.add_argument("-b", "--write-backups-every", dest="write_backups_every", default=100, type=int,
+                       help="Number of iterations to go between writing backups of program state")
+        p.add_argument("-S", "--write-state-every", dest="write_state_every", default=10, type=int,
+                       help="Number of iterations between writing program state to disk")
+        p.add_argument("-B", "--burnin-samples", dest="burnin_samples", default=1000, type=int, help="Number of burnin samples")
+        p.add_argument("-s", "--mcmc-samples", dest="mcmc_samples", default=2500, type=int, help="Number of MCMC samples")
+        p.add_argument("-i", "--mh-iterations", dest="mh_iterations", default=5000, type=int,
+                       help="Number of Metropolis-Hastings iterations")
+        p.add_argument("-r", "--random-seed", dest="random_seed", type=int, help="Random seed for initializing MCMC sampler")
+        p.add_argument("-t", "--tmp-dir", dest="tmp_dir", help="Path to directory for temporary files")
+        p.add_argument("-p", "--params", dest="params_file", help="JSON file listing run parameters, generated by the parser")
+        p.add_argument("ssm_file", help="File listing SSMs. For proper format, see README.md.")
+        p.add_argument("cnv_file", help="File listing CNVs. For proper format, see README.md.")
+    return p
+
+
+def run(safe_to_exit, run_succeeded, config, argv=None):
+    install_pickle_aliases()
+    known, _ = create_argparser(full=False).parse_known_args(argv)
+    orig_dir = os.getcwd()
+    if known.output_dir is not None:
+        os.makedirs(known.output_dir, exist_ok=True)
+        os.chdir(known.output_dir)
+    state_manager = StateManager()
+    backup_manager = BackupManager([StateManager.default_last_state_fn, TreeWriter.default_archive_fn])
+    if state_manager.state_exists():
+        logmsg("Resuming existing run. Ignoring command-line parameters (except --output-dir).")
+        resume_existing_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config)
+        return
+    args = create_argparser().parse_args(argv)
+    paths = {}
+    for key in ("ssm_file", "cnv_file", "params_file", "tmp_dir"):
+        v = getattr(args, key)
+        paths[key] = os.path.normpath(os.path.join(orig_dir, v)) if v is not None else None
+    for key in ("ssm_file", "cnv_file"):
+        try:
+            open(paths[key]).close()
+        except OSError as e:
+            sys.stderr.write(str(e) + "\n")
+            sys.exit(1)
+    start_new_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config, paths["ssm_file"], paths["cnv_file"],
+                  paths["params_file"], burnin_samples=args.burnin_samples, num_samples=args.mcmc_samples,
+                  mh_itr=args.mh_iterations, mh_std=100, write_state_every=args.write_state_every,
+                  write_backups_every=args.write_backups_every, rand_seed=args.random_seed, tmp_dir=paths["tmp_dir"])
+
+
+def remove_tmp_files(tmp_dir):
+    if tmp_dir is None:
+        return
+    for fn in get_c_fnames(tmp_dir):
+        rm_safely(fn)
+    try:
+        os.rmdir(tmp_dir)
+    except OSError:
+        pass
+
+
+def main(argv=None):
+    if argv is None:
+        argv = sys.argv[1:]
+    if "-h" in argv or "--help" in argv:
+        create_argparser().print_help()
+        sys.exit()
+    safe_to_exit, run_succeeded = threading.Event(), threading.Event()
+    config = {"tmp_dir": None}
+
+    def on_signal(signo, _frame):
+        logmsg("Signal %s received." % signo, sys.stderr)
+        safe_to_exit.wait()
+        remove_tmp_files(config["tmp_dir"])
+        logmsg("Exiting now.")
+        sys.exit(3)
+
+    signal.signal(signal.SIGTERM, on_signal)
+    signal.signal(signal.SIGINT, on_signal)
+    worker = threading.Thread(target=run, args=(safe_to_exit, run_succeeded, config, argv), daemon=True)
+    worker.start()
+    while worker.is_alive():
+        worker.join(10)
+    remove_tmp_files(config["tmp_dir"])
+    if run_succeeded.is_set():
+        logmsg("Run succeeded.")
+        sys.exit(0)
+    logmsg("Run failed.")
+    sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

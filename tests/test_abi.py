@@ -48,7 +48,7 @@ def test_no_oracle_or_torch_in_the_product():
             if f.endswith(".py"):
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert not re.search(r"^\s*(from|import)\s+torch\b", src, flags=re.M), f
-                assert "liboracle" not in src and "_ref" not in src, f
+                assert "liboracle" not in src and "oracle/_ref" not in src and "libpwgs_ref" not in src, f
             else:
                 assert not re.search(r'#include\s+"[^"]*oracle', src), f
 
