@@ -179,6 +179,23 @@ def time_reference(s, chains, iters_sample, mh_std=MH_STD):
     return dict(rate=chains * iters_sample / loop, t_parse=t_parse, t_run=t_run, accept=ar)
 
 
+def reduce_max_over_ranks(x, world, device):
+    """Every multi-GPU time is the MAX over ranks (one chain per rank; the job is as slow as its slowest chain)."""
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def chain_stream(rank, phase, k):
+    """Philox stream id of step k of a rank's chain in a bench phase (0 warm-up, 1 value, 2 e2e): distinct across ranks, so the
+    N chains of a multi-GPU run are independent replicas like multievolve's (multievolve.py:104-105 seeds)."""
+    return 1000 * rank + 100 * phase + k
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -244,11 +261,7 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return reduce_max_over_ranks(x, world, dev)
 
     from phylowgs_b200 import synth
     eng = P.Engine(device=local_rank, **synth.data_kwargs(s))
@@ -266,7 +279,7 @@ def main():
     for w in range(args.warmup):
         with torch.cuda.stream(ext):
             flush.zero_()                                                   # also loads torch's fill kernel before the timed region
-        eng.mh_launch(MH_ITR, mh_std, seed, 1000 * rank + w)
+        eng.mh_launch(MH_ITR, mh_std, seed, chain_stream(rank, 0, w))
         eng.mh_wait(fetch=False)
     fp64_peak = P.fp64_peak(local_rank)                                 # DFMA thread-instr/s, measured on this GPU now
 
@@ -284,7 +297,7 @@ def main():
         for k in range(args.steps):
             tw0 = time.perf_counter()
             flush.zero_()                                               # L2 flush between timed steps (inside the bracket)
-            eng.mh_launch(MH_ITR, mh_std, seed, 1000 * rank + 100 + k)
+            eng.mh_launch(MH_ITR, mh_std, seed, chain_stream(rank, 1, k))
             r = eng.mh_wait(fetch=False)
             kernel_ms.append(r["kernel_ms"])
             ratios.append(r["ratio"])
@@ -307,7 +320,7 @@ def main():
     t0 = time.perf_counter()
     for k in range(args.steps):
         eng.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
-        eng.mh_run(MH_ITR, mh_std, seed, 1000 * rank + 200 + k)
+        eng.mh_run(MH_ITR, mh_std, seed, chain_stream(rank, 2, k))
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = n_gpus * args.steps * MH_ITR / e2e_s
