@@ -330,7 +330,7 @@ struct MhParams {
     double *phi_out, *pi_out;           // [K*T] state on exit
     int *acc_out;                       // accepted proposals
     double *llh_out;                    // multi_param_post of the final state
-    int iters, max_batch;               // max_batch: power of two in 1..16
+    int iters, max_batch;               // max_batch: power of two in 1..PWGS_MAX_BATCH
     int stage;                          // 1: each CTA copies its slice of the data into shared memory once (normal case)
     int distributed;                    // 1: proposals two batches ahead are drawn once per chain and shared through `ring`
     double mh_std;
@@ -923,23 +923,26 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         }
         {
             const double *pp = p.partials + (size_t)parity * PWGS_MAX_BATCH * cpc;
-            const int b0 = warp, b1 = warp + MH_CWARPS;                          // MAXB <= 2 * MH_CWARPS
-            double v0[5], v1[5];
+#pragma unroll 1
+            for (int bq = warp; bq < b_nb; bq += 2 * MH_CWARPS) {                // two proposals per warp and pass
+                const int b0 = bq, b1 = bq + MH_CWARPS;
+                double v0[5], v1[5];
 #pragma unroll
-            for (int i = 0; i < 5; i++) {
-                const int r = lane + 32 * i;
-                v0[i] = (b0 < b_nb && r < cpc) ? __ldcg(pp + (size_t)b0 * cpc + r) : 0.0;
-                v1[i] = (b1 < b_nb && r < cpc) ? __ldcg(pp + (size_t)b1 * cpc + r) : 0.0;
-            }
-            double t0 = 0.0, t1 = 0.0;
+                for (int i = 0; i < 5; i++) {
+                    const int r = lane + 32 * i;
+                    v0[i] = (r < cpc) ? __ldcg(pp + (size_t)b0 * cpc + r) : 0.0;
+                    v1[i] = (b1 < b_nb && r < cpc) ? __ldcg(pp + (size_t)b1 * cpc + r) : 0.0;
+                }
+                double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-            for (int i = 0; i < 5; i++) { t0 += v0[i]; t1 += v1[i]; }
-            for (int r = lane + 160; r < cpc; r += 32) {                         // chains wider than 160 CTAs (not on B200)
-                if (b0 < b_nb) t0 += __ldcg(pp + (size_t)b0 * cpc + r);
-                if (b1 < b_nb) t1 += __ldcg(pp + (size_t)b1 * cpc + r);
+                for (int i = 0; i < 5; i++) { t0 += v0[i]; t1 += v1[i]; }
+                for (int r = lane + 160; r < cpc; r += 32) {                     // chains wider than 160 CTAs (not on B200)
+                    t0 += __ldcg(pp + (size_t)b0 * cpc + r);
+                    if (b1 < b_nb) t1 += __ldcg(pp + (size_t)b1 * cpc + r);
+                }
+                t0 = warp_sum(t0); t1 = warp_sum(t1);
+                if (lane == 0) { S.llh[b0] = t0; if (b1 < b_nb) S.llh[b1] = t1; }
             }
-            t0 = warp_sum(t0); t1 = warp_sum(t1);
-            if (lane == 0) { if (b0 < b_nb) S.llh[b0] = t0; if (b1 < b_nb) S.llh[b1] = t1; }
         }
         if (fetch) {
             double *dst = S.prop_pi(cur ^ 1);
