@@ -94,6 +94,10 @@ int pwgs_mh_wait(pwgs_ctx *ctx, double *phi_out, double *pi_out, double *accept_
  * (tssb.py:111,128 -> alleles.py:52 -> data.py:26-62): out[r*K + k] = log-likelihood of datum rows[r]
  * if it sat in node k of the current tree (all K candidates at once). */
 int pwgs_llh_rows(pwgs_ctx *ctx, int n_rows, const int32_t *rows, int semantics, double *out);
+/* The same for a subset of candidate nodes: out[r*n_cols + c] for node cols[c] (cols == NULL: all K nodes).  After find_node
+ * spawns nodes (tssb.py:353-361) only the new nodes' columns are missing: a spawn splits its parent's pi but leaves every
+ * existing node's phi, and therefore every existing grid entry, unchanged. */
+int pwgs_llh_block(pwgs_ctx *ctx, int n_rows, const int32_t *rows, int n_cols, const int32_t *cols, int semantics, double *out);
 
 /* semantics MH: multi_param_post of the current state (mh.cpp:147-166).
  * semantics PY: the data term of TSSB.complete_data_log_likelihood (tssb.py:404-410, alleles.py:55-56). */

@@ -71,7 +71,7 @@ struct pwgs_ctx {
     DevBuf<unsigned long long> counter, prof;
     bool opt_prof = false;
     unsigned long long prof_host[16] = {0};
-    DevBuf<int> acc_out, rows, abort_flag;
+    DevBuf<int> acc_out, rows, cols, abort_flag;
     DevBuf<MhParams> plist;
     int opt_batch = PWGS_MAX_BATCH, opt_ctas = 0, opt_stage = 1, opt_dist = -1;
     bool launched = false;
@@ -128,7 +128,7 @@ int pwgs_destroy(pwgs_ctx *c)
     c->code_tmp.release(); c->enode_tmp.release(); c->pos.release(); c->w_a.release(); c->w_d.release(); c->w_code.release();
     c->w_enode.release(); c->overflow.release(); c->ecoef_tmp.release(); c->w_ecoef.release(); c->w_lbc.release(); c->w_mu_r.release();
     c->partials.release(); c->ring.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
-    c->counter.release(); c->prof.release(); c->acc_out.release(); c->abort_flag.release(); c->rows.release(); c->plist.release();
+    c->counter.release(); c->prof.release(); c->acc_out.release(); c->abort_flag.release(); c->cols.release(); c->rows.release(); c->plist.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -468,25 +468,35 @@ int pwgs_mh_run(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_t s
 }
 
 // ------------------------------------------------------------------ likelihood grid / totals
-int pwgs_llh_rows(pwgs_ctx *c, int n_rows, const int32_t *rows, int semantics, double *out)
+int pwgs_llh_block(pwgs_ctx *c, int n_rows, const int32_t *rows, int n_cols, const int32_t *cols, int semantics, double *out)
 {
     if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
     if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called first");
     if (n_rows < 0 || (n_rows > 0 && (!rows || !out))) return fail(PWGS_EINVAL, "rows/out NULL");
     if (semantics != PWGS_SEM_MH && semantics != PWGS_SEM_PY) return fail(PWGS_EINVAL, "unknown semantics");
-    if (n_rows == 0) return PWGS_OK;
+    if (cols == nullptr) n_cols = c->K;
+    if (n_cols < 0) return fail(PWGS_EINVAL, "n_cols must be >= 0");
+    if (n_rows == 0 || n_cols == 0) return PWGS_OK;
     for (int r = 0; r < n_rows; r++) if (rows[r] < 0 || rows[r] >= c->D) return fail(PWGS_EINVAL, "row index out of range");
+    if (cols) for (int k = 0; k < n_cols; k++) if (cols[k] < 0 || cols[k] >= c->K) return fail(PWGS_EINVAL, "node index out of range");
     CUDA_TRY(cudaSetDevice(c->device));
-    size_t total = (size_t)n_rows * c->K;
+    size_t total = (size_t)n_rows * n_cols;
     CUDA_TRY(c->rows.upload(rows, n_rows, c->stream));
+    if (cols) CUDA_TRY(c->cols.upload(cols, n_cols, c->stream));
     CUDA_TRY(c->scratch.alloc(total));
-    pair_llh_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(data_view(c), tree_view(c), 0, n_rows, c->rows.p, semantics,
-                                                                            kLogTinyMh, kLogTinyPy, kLogQuarter, c->scratch.p);
+    pair_llh_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(data_view(c), tree_view(c), 0, n_rows, c->rows.p, n_cols,
+                                                                            cols ? c->cols.p : nullptr, semantics, kLogTinyMh, kLogTinyPy,
+                                                                            kLogQuarter, c->scratch.p);
     CUDA_TRY(cudaGetLastError());
     c->n_launches++;
     CUDA_TRY(cudaMemcpyAsync(out, c->scratch.p, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PWGS_OK;
+}
+
+int pwgs_llh_rows(pwgs_ctx *c, int n_rows, const int32_t *rows, int semantics, double *out)
+{
+    return pwgs_llh_block(c, n_rows, rows, 0, nullptr, semantics, out);
 }
 
 int pwgs_total_llh(pwgs_ctx *c, int semantics, double *out)
@@ -500,7 +510,7 @@ int pwgs_total_llh(pwgs_ctx *c, int semantics, double *out)
     if (semantics != PWGS_SEM_PY) return fail(PWGS_EINVAL, "unknown semantics");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(c->scratch.alloc((size_t)c->D + 1));
-    pair_llh_kernel<<<(c->D + 127) / 128, 128, 0, c->stream>>>(data_view(c), tree_view(c), 1, c->D, nullptr, semantics,
+    pair_llh_kernel<<<(c->D + 127) / 128, 128, 0, c->stream>>>(data_view(c), tree_view(c), 1, c->D, nullptr, 0, nullptr, semantics,
                                                                kLogTinyMh, kLogTinyPy, kLogQuarter, c->scratch.p);
     CUDA_TRY(cudaGetLastError());
     sum_kernel<<<1, 1024, 0, c->stream>>>(c->D, c->scratch.p, c->scratch.p + c->D);

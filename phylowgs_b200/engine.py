@@ -86,6 +86,14 @@ class Engine:
         check(_lib.load().pwgs_llh_rows(self._h, len(rows), p_i32(rows), int(semantics), p_f64(out)))
         return out
 
+    def llh_block(self, rows, cols, semantics=SEM_PY):
+        rows, cols = i32(rows), i32(cols)
+        out = np.zeros((len(rows), len(cols)))
+        if out.size == 0:
+            return out
+        check(_lib.load().pwgs_llh_block(self._h, len(rows), p_i32(rows), len(cols), p_i32(cols), int(semantics), p_f64(out)))
+        return out
+
     def total_llh(self, semantics=SEM_PY):
         v = C.c_double(0)
         check(_lib.load().pwgs_total_llh(self._h, int(semantics), C.byref(v)))

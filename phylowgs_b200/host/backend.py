@@ -57,6 +57,9 @@ class Backend(object):
     def llh_rows(self, rows):
         raise NotImplementedError
 
+    def llh_block(self, rows, cols):
+        raise NotImplementedError
+
     def total_llh(self):
         raise NotImplementedError
 
@@ -90,6 +93,9 @@ class GpuBackend(Backend):
 
     def llh_rows(self, rows):
         return self.engine.llh_rows(rows, SEM_PY)
+
+    def llh_block(self, rows, cols):
+        return self.engine.llh_block(rows, cols, SEM_PY)
 
     def total_llh(self):
         return self.engine.total_llh(SEM_PY)

@@ -19,6 +19,9 @@ class OracleBackend(Backend):
     def llh_rows(self, rows):
         return O.llh_rows(self.data, self.tree, rows, O.SEM_PY)
 
+    def llh_block(self, rows, cols):
+        return O.llh_rows(self.data, self.tree, rows, O.SEM_PY)[:, np.asarray(cols, dtype=int)]
+
     def total_llh(self):
         return O.total_llh(self.data, self.tree, O.SEM_PY)
 
