@@ -224,12 +224,20 @@ class TSSB(object):
                 return entry["node"], path
             u = (u - entry["main"]) / (1.0 - entry["main"])
             if depth > 0:
-                while not entry["children"] or (1.0 - np.prod(1.0 - entry["sticks"])) < u:
+                # right edges of the children's intervals as a running product (plain floats: this is the hot host loop)
+                rem, edges = 1.0, []
+                for s in (entry["sticks"][:, 0].tolist() if len(entry["sticks"]) else ()):
+                    rem *= 1.0 - s
+                    edges.append(1.0 - rem)
+                while not edges or edges[-1] < u:
                     self._new_child(entry, depth)
-                edges = sticks_to_edges(entry["sticks"])
-                index = int(np.sum(u > edges))
-                edges = np.hstack([0.0, edges])
-                u = (u - edges[index]) / (edges[index + 1] - edges[index])
+                    rem *= 1.0 - float(entry["sticks"][-1, 0])
+                    edges.append(1.0 - rem)
+                index = 0
+                while edges[index] < u:
+                    index += 1
+                left = edges[index - 1] if index else 0.0
+                u = (u - left) / (edges[index] - left)
             else:
                 index = 0                                   # the root always descends into its first child (tssb.py:369-371)
             path.append(index)

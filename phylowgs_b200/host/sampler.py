@@ -18,17 +18,17 @@ from .model import EPS
 
 
 def _path_cmp(cur, new):
-    """Ordering of two child-index paths in the stick-breaking layout of [0,1) (tssb.py:84-94: zero-padded strings, py2 cmp).
-    < 0: the candidate lies left of the current node's region, so the lower bound moves up; otherwise the upper bound moves down."""
+    """Ordering of two child-index paths in the stick-breaking layout of [0,1) (tssb.py:84-94: the reference compares the
+    zero-padded "%03d" strings with py2 cmp(s2, s1); for fewer than 1000 children per node that is the lexicographic order of
+    the index tuples).  < 0: the candidate lies left of the current node, so the lower bound moves up; else the upper bound."""
     if not cur and not new:
         return 0
     if not cur:
         return 1
     if not new:
         return -1
-    s1 = "".join("%03d" % i for i in cur)
-    s2 = "".join("%03d" % i for i in new)
-    return (s2 > s1) - (s2 < s1)
+    a, b = tuple(cur), tuple(new)
+    return (b > a) - (b < a)
 
 
 class _Grid(object):
@@ -108,15 +108,18 @@ def resample_assignments(tssb):
     rng, root_entry = tssb.rng, tssb.root
     grid = _Grid(tssb)
     n_ssm = tssb.backend.n_ssm
+    paths = {}
     for n in range(tssb.num_data):
         datum = tssb.data[n]
         cur = tssb.assignments[n]
-        # child-index path of the current node (tssb.py:101-107)
-        indices, entry = [], root_entry
-        for anc in cur.get_ancestors()[1:]:
-            k = next(i for i, c in enumerate(entry["children"]) if c["node"] is anc)
-            indices.append(k)
-            entry = entry["children"][k]
+        indices = paths.get(id(cur))
+        if indices is None:                                 # child-index path of the node (tssb.py:101-107); spawns append
+            indices, entry = [], root_entry                 # children at the end, so paths stay valid through the sweep
+            for anc in cur.get_ancestors()[1:]:
+                k = next(i for i, c in enumerate(entry["children"]) if c["node"] is anc)
+                indices.append(k)
+                entry = entry["children"][k]
+            paths[id(cur)] = indices
         lo, hi = 0.0, 1.0
         llh_s = np.log(rng.rand()) + grid.get(n, cur)
         while True:

@@ -40,3 +40,40 @@ def test_gpu_chain_reproduces_oracle_chain(gpu_lib, tmp_path, name, iterations, 
         assert o["acc"] == g["acc"]
         assert np.max(np.abs(o["phi"] - g["phi"])) < 1e-9
         assert abs(o["llh"] - g["llh"]) <= 1e-9 * abs(o["llh"])
+
+
+def test_gpu_chain_recovers_simulated_subclones(gpu_lib, tmp_path):
+    """phylowgs_sims emptysim.4.100.50: three cancerous populations of 50 SSMs each at depth 100 (truth is implied by the block
+    structure).  A short chain on the GPU must put the posterior-mean cellular prevalence of every SSM
+    close to its block's 2*VAF and use a handful of major populations (nodes holding >= 5% of the SSMs, the kind of node the
+    reference's post-processing keeps).  Stated tolerance: per-SSM RMSE <= 0.06, modal number of major populations in 2..5."""
+    ssm, cnv = os.path.join(cases.GOLDEN, "emptysim.4.100.50.ssm.txt"), empty_cnv(tmp_path)
+    tssb, n_ssms, n_cnvs = chain_util.new_chain(ssm, cnv, gpu_backend, seed=3)
+    rows = [l.split("\t") for l in open(ssm).read().strip().split("\n")[1:]]
+    a = np.array([int(r[2]) for r in rows], dtype=float)
+    d = np.array([int(r[3]) for r in rows], dtype=float)
+    truth = np.repeat([2 * (1 - a[i:i + 50] / d[i:i + 50]).mean() for i in (0, 50, 100)], 50)
+    burn, keep = 120, 120
+    phi_sum, populated = np.zeros(n_ssms), []
+    mh_std = 100.0
+    from phylowgs_b200.host.params import metropolis
+    for it in range(burn + keep):
+        tssb.resample_assignments()
+        tssb.cull_tree()
+        acc = float(metropolis(tssb, 1000, mh_std, 0, n_ssms, n_cnvs, "", "", 3, 1, ".", stream=it))
+        if acc < 0.08 and mh_std < 10000:
+            mh_std *= 2.0
+        if 0.5 < acc < 0.99:
+            mh_std /= 2.0
+        tssb.resample_sticks()
+        tssb.resample_stick_orders()
+        tssb.resample_hypers()
+        if it >= burn:
+            phi_sum += np.array([float(tssb.assignments[n].params[0]) for n in range(n_ssms)])
+            populated.append(sum(1 for nd in tssb.get_nodes() if nd.num_local_data() >= 0.05 * n_ssms))
+    tssb.backend.close()
+    post = phi_sum / keep
+    rmse = float(np.sqrt(np.mean((post - truth) ** 2)))
+    mode = int(np.bincount(populated).argmax())
+    assert rmse <= 0.06, (rmse, post[::25], truth[::25])
+    assert 2 <= mode <= 5, populated
