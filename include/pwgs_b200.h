@@ -109,7 +109,7 @@ int pwgs_get_lbc(pwgs_ctx *ctx, double *out /* [D*T] log_bin_coeff(d,a), mh.cpp:
  * Pass NULL arrays to query M only. */
 int pwgs_get_data_states(pwgs_ctx *ctx, int32_t *M, int32_t *ssm_of_m, int32_t *coef);
 
-/* Tuning knobs: "mh_batch" (largest speculative batch of proposals per grid barrier: 1, 2, 4, 8, 16 or 32 = default; the kernel
+/* Tuning knobs: "mh_batch" (largest speculative batch of proposals per grid barrier: a power of two in 1..128 = default; the kernel
  * adapts the actual batch to the running acceptance rate) and "mh_ctas" (CTAs per chain, 0 = all SMs). */
 int pwgs_set_option(pwgs_ctx *ctx, const char *name, int64_t value);
 int pwgs_get_option(pwgs_ctx *ctx, const char *name, int64_t *value);

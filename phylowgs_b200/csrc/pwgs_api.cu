@@ -565,7 +565,7 @@ int pwgs_set_option(pwgs_ctx *c, const char *name, int64_t value)
     if (!c || !name) return fail(PWGS_EINVAL, "NULL argument");
     std::string n(name);
     if (n == "mh_batch") {
-        if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32) return fail(PWGS_EINVAL, "mh_batch must be 1, 2, 4, 8, 16 or 32");
+        if (value < 1 || value > PWGS_MAX_BATCH || (value & (value - 1))) return fail(PWGS_EINVAL, "mh_batch must be a power of two in 1..128");
         c->opt_batch = (int)value;
     } else if (n == "mh_ctas") {
         if (value < 0) return fail(PWGS_EINVAL, "mh_ctas must be >= 0");

@@ -362,7 +362,7 @@ struct MhSmem {
     __device__ __forceinline__ double *prop_phi(int b) const { return buf0 + b * bufstride + o_phi; }
     __device__ __forceinline__ double *hast(int b) const { return buf0 + b * bufstride + o_hast; }
     __device__ __forceinline__ double *logr(int b) const { return buf0 + b * bufstride + o_logr; }
-    double *red;                                    // [MH_BU][MH_CWARPS]
+    double *red;                                    // [nb][warps per proposal group]: per-warp sums of the current batch
     double *llh;                                    // [MAXB]
     double *pscratch;                               // [2K] producer warp: pi1 and phi1 of the proposal being drawn
     volatile int *ctl;                              // producer mailbox, see MhCtl
@@ -374,7 +374,8 @@ __host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return 
 __host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
 {
     size_t KT = (size_t)K * T;
-    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + MH_BU * MH_CWARPS + maxb + 2 * K;
+    const size_t red = (size_t)maxb > MH_BU * MH_CWARPS ? (size_t)maxb : MH_BU * MH_CWARPS;
+    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 2 * K;
 }
 __host__ __device__ inline size_t mh_smem_ints(int K) { return CTL_WORDS + 2 * (size_t)K; }
 
@@ -556,13 +557,11 @@ __host__ __device__ inline size_t mh_stage_bytes(int pchunk, int cchunk, int T, 
 // the group's stride and accumulating BU sums, so that every load / int->fp64 conversion is shared by BU proposals and the BU
 // independent chains of logarithms overlap in the FP64 pipe.  Leaves red[bb][warp] = the warp's sum for proposal g*BU+bb.
 template <int BU, class Slice>
-__device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S, const Slice &sl, int cur, int nb, int warp, int lane)
+__device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S, const Slice &sl, int cur, int wpg, int role, int g, int lane)
 {
+    // proposal group g (proposals g*BU .. g*BU+BU-1) is evaluated by wpg warps; this warp is number `role` of them
     const int T = p.T, KT = p.K * T;
-    // group g = warps [g*wpg, (g+1)*wpg); inside a group the warp roles are rotated by g so that the warps holding the expensive
-    // head of the sorted CNV list land on different SM sub-partitions (warp id % 4) in different groups
-    const int wpg = MH_CWARPS / (nb / BU), tpg = wpg * 32, g = warp / wpg;
-    const int lt = ((warp - g * wpg + g) % wpg) * 32 + lane;
+    const int tpg = wpg * 32, lt = role * 32 + lane;
     const double *bphi = S.prop_phi(cur) + (g * BU) * KT;
     double acc[BU];
 #pragma unroll
@@ -696,7 +695,7 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
 #pragma unroll
     for (int bb = 0; bb < BU; bb++) {
         const double t = warp_sum(acc[bb]);
-        if (lane == 0) S.red[bb * MH_CWARPS + warp] = t;
+        if (lane == 0) S.red[(g * BU + bb) * wpg + role] = t;
     }
 }
 
@@ -768,7 +767,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         S.state0 = q; q += 2 * S.statestride;
         S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = MAXB * KT; S.o_hast = 2 * MAXB * KT; S.o_logr = 2 * MAXB * KT + MAXB * T;
         S.buf0 = q; q += 2 * S.bufstride;
-        S.red = q; q += MH_BU * MH_CWARPS; S.llh = q; q += MAXB;
+        S.red = q; q += (MAXB > MH_BU * MH_CWARPS ? MAXB : MH_BU * MH_CWARPS); S.llh = q; q += MAXB;
         S.pscratch = q; q += 2 * K;
         S.ctl = (volatile int *)q; S.tin = (int *)q + CTL_WORDS; S.tout = S.tin + K;
     }
@@ -865,18 +864,28 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
 
         // ---------------- likelihood (param_post) of the CTA's slice for every proposal of the batch
         const int bu = b_nb >= MH_BU ? MH_BU : 1;      // thread groups of MH_BU proposals, or one proposal per group
-        if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, b_nb, warp, lane); else mh_likelihood<1>(p, S, sl, cur, b_nb, warp, lane);
+        const int ngroups = b_nb / bu;                  // proposal groups of the batch
+        const int wpg = ngroups <= MH_CWARPS ? MH_CWARPS / ngroups : 1;
+        if (ngroups <= MH_CWARPS) {
+            // warps [g*wpg, (g+1)*wpg) share group g; roles are rotated by g so that the warps holding the expensive head of the
+            // sorted CNV list land on different SM sub-partitions (warp id % 4) in different groups
+            const int gq = warp / wpg, role = (warp - gq * wpg + gq) % wpg;
+            if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, wpg, role, gq, lane); else mh_likelihood<1>(p, S, sl, cur, wpg, role, gq, lane);
+        } else {
+#pragma unroll 1
+            for (int gq = warp; gq < ngroups; gq += MH_CWARPS)                  // large batches: several groups per warp, in turn
+                mh_likelihood<MH_BU>(p, S, sl, cur, 1, 0, gq, lane);
+        }
         consumer_sync();
         MH_PROF(0);
 
         // ---------------- publish the CTA's partial sums and arrive at the chain barrier (release)
         const int parity = g & 1;
         if (warp == 0) {
-            if (lane < b_nb) {
-                const int wpg = MH_CWARPS / (b_nb / bu), gg = lane / bu, bb = lane - gg * bu;     // warps per thread group
+            for (int b = lane; b < b_nb; b += 32) {
                 double t = 0.0;
-                for (int w2 = gg * wpg; w2 < (gg + 1) * wpg; w2++) t += S.red[bb * MH_CWARPS + w2];
-                p.partials[((size_t)parity * PWGS_MAX_BATCH + lane) * cpc + rank] = t;
+                for (int r = 0; r < wpg; r++) t += S.red[b * wpg + r];
+                p.partials[((size_t)parity * PWGS_MAX_BATCH + b) * cpc + rank] = t;
             }
             __syncwarp();
             if (lane == 0) {
@@ -961,14 +970,17 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         if (j < 0) {
             cur_llh = S.llh[0];
         } else {
-            bool ok = false;
-            if (lane < b_nb) {
-                double a = S.llh[lane] - cur_llh;
-                for (int tp = 0; tp < T; tp++) a += S.hast(cur)[lane * T + tp];
-                ok = S.logr(cur)[lane] < a;
+            for (int base = 0; base < b_nb && sel < 0; base += 32) {
+                const int b = base + lane;
+                bool ok = false;
+                if (b < b_nb) {
+                    double a = S.llh[b] - cur_llh;
+                    for (int tp = 0; tp < T; tp++) a += S.hast(cur)[b * T + tp];
+                    ok = S.logr(cur)[b] < a;
+                }
+                const unsigned m = __ballot_sync(PWGS_FULL_MASK, ok);
+                if (m) sel = base + __ffs(m) - 1;
             }
-            const unsigned m = __ballot_sync(PWGS_FULL_MASK, ok);
-            sel = m ? __ffs(m) - 1 : -1;
         }
         pc[7]++;
         g++;

@@ -76,7 +76,7 @@ def test_bundled_golden_cases(oracle, gpu_lib):
             assert rel(eng.total_llh(gpu_lib.SEM_PY), oracle.total_llh(data, tree, oracle.SEM_PY)) < RTOL
 
 
-@pytest.mark.parametrize("batch", [1, 4, 32])
+@pytest.mark.parametrize("batch", [1, 4, 32, 128])
 @pytest.mark.parametrize("ctas", [1, 3, 0])
 @pytest.mark.parametrize("stage", [1, 0])
 @pytest.mark.parametrize("dist", [-1, 1])
