@@ -311,8 +311,9 @@ __global__ void sum_kernel(int n, const double *__restrict__ x, double *out)
 }
 
 // ============================================================================ K1
-#define MH_CWARPS 8                      // consumer warps (likelihood + bookkeeping): 2 per SM sub-partition, 224 registers each,
-                                         // so that 8 chains of fp64 logarithms per thread stay in registers and overlap
+#define MH_CWARPS 11                     // consumer warps (likelihood + bookkeeping); with the producer warp that is 12 warps = 3 per
+                                         // SM sub-partition, the most that fit at 168 registers (8 interleaved chains of fp64 logarithms per thread)
+#define MH_GWARPS 8                      // of which this many (a power of two) share the proposal groups of a small batch
 #define MH_CONSUMERS (MH_CWARPS * 32)
 #define MH_THREADS (MH_CONSUMERS + 32)   // + one producer warp (proposal draws for the ring)
 #define MH_BU 4                          // proposals evaluated per thread in one pass over its data
@@ -374,7 +375,7 @@ __host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return 
 __host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
 {
     size_t KT = (size_t)K * T;
-    const size_t red = (size_t)maxb > MH_BU * MH_CWARPS ? (size_t)maxb : MH_BU * MH_CWARPS;
+    const size_t red = (size_t)maxb > MH_BU * MH_GWARPS ? (size_t)maxb : MH_BU * MH_GWARPS;
     return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 2 * K;
 }
 __host__ __device__ inline size_t mh_smem_ints(int K) { return CTL_WORDS + 2 * (size_t)K; }
@@ -767,7 +768,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         S.state0 = q; q += 2 * S.statestride;
         S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = MAXB * KT; S.o_hast = 2 * MAXB * KT; S.o_logr = 2 * MAXB * KT + MAXB * T;
         S.buf0 = q; q += 2 * S.bufstride;
-        S.red = q; q += (MAXB > MH_BU * MH_CWARPS ? MAXB : MH_BU * MH_CWARPS); S.llh = q; q += MAXB;
+        S.red = q; q += (MAXB > MH_BU * MH_GWARPS ? MAXB : MH_BU * MH_GWARPS); S.llh = q; q += MAXB;
         S.pscratch = q; q += 2 * K;
         S.ctl = (volatile int *)q; S.tin = (int *)q + CTL_WORDS; S.tout = S.tin + K;
     }
@@ -865,12 +866,15 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         // ---------------- likelihood (param_post) of the CTA's slice for every proposal of the batch
         const int bu = b_nb >= MH_BU ? MH_BU : 1;      // thread groups of MH_BU proposals, or one proposal per group
         const int ngroups = b_nb / bu;                  // proposal groups of the batch
-        const int wpg = ngroups <= MH_CWARPS ? MH_CWARPS / ngroups : 1;
-        if (ngroups <= MH_CWARPS) {
-            // warps [g*wpg, (g+1)*wpg) share group g; roles are rotated by g so that the warps holding the expensive head of the
-            // sorted CNV list land on different SM sub-partitions (warp id % 4) in different groups
-            const int gq = warp / wpg, role = (warp - gq * wpg + gq) % wpg;
-            if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, wpg, role, gq, lane); else mh_likelihood<1>(p, S, sl, cur, wpg, role, gq, lane);
+        const int wpg = ngroups <= MH_GWARPS ? MH_GWARPS / ngroups : 1;
+        if (ngroups <= MH_GWARPS) {
+            // small batch: the first MH_GWARPS warps split into the groups, warps [g*wpg, (g+1)*wpg) share group g; roles are
+            // rotated by g so that the warps holding the expensive head of the sorted CNV list land on different SM
+            // sub-partitions (warp id % 4) in different groups
+            if (warp < MH_GWARPS) {
+                const int gq = warp / wpg, role = (warp - gq * wpg + gq) % wpg;
+                if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, wpg, role, gq, lane); else mh_likelihood<1>(p, S, sl, cur, wpg, role, gq, lane);
+            }
         } else {
 #pragma unroll 1
             for (int gq = warp; gq < ngroups; gq += MH_CWARPS)                  // large batches: several groups per warp, in turn
