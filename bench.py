@@ -82,7 +82,7 @@ class ClockSampler:
     """SM clock + throttle reasons sampled through NVML from a host thread DURING the timed region (the recipe's clocks line;
     NVML instead of spawning nvidia-smi so that starting the sampler does not itself disturb the timed kernels)."""
 
-    def __init__(self, index, period_s=0.15):
+    def __init__(self, index, period_s=0.03):
         import threading
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -177,6 +177,27 @@ def time_reference(s, chains, iters_sample, mh_std=MH_STD):
         ar = float(open(os.path.join(wd, "c_mh_ar_0.txt")).read())
     loop = max(t_run - t_parse, 1e-9)
     return dict(rate=chains * iters_sample / loop, t_parse=t_parse, t_run=t_run, accept=ar)
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one MH-kernel launch, from the newest committed `ncu --set full` summary
+    under profiles/ (a number measured under the profiler, quoted, never re-measured here); None if there is none."""
+    import glob
+    import re
+    best = None
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_mh_kernel_ncu_full.txt"))):
+        rd = wr = None
+        for line in open(fn):
+            m = re.match(r"dram__bytes_(read|write)\.sum\s+(\S+)\s+(\S+)", line)
+            if m:
+                v = float(m.group(3)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(2), float("nan"))
+                if m.group(1) == "read":
+                    rd = v
+                else:
+                    wr = v
+        if rd is not None and wr is not None:
+            best = rd + wr
+    return best
 
 
 def reduce_max_over_ranks(x, world, device):
@@ -331,9 +352,6 @@ def main():
         tot = max(sum(pc[:7]), 1)
         print("phase cycles (CTA 0, last launch): " + ", ".join("%s=%d (%.1f%%)" % (n, v, 100.0 * v / tot) for n, v in zip(names[:7], pc[:7]))
               + ", batches=%d, cycles/batch=%.0f" % (pc[7], tot / max(pc[7], 1)), file=sys.stderr)
-        dn = ["gamma", "normalise", "subtree", "lgamma_log", "reduce_tail"]
-        dv = [eng.get_option("mh_prof_%d" % (8 + i)) for i in range(5)]
-        print("draw cycles per batch (warp 0): " + ", ".join("%s=%.0f" % (n, v / max(pc[7], 1)) for n, v in zip(dn, dv)), file=sys.stderr)
     if rank != 0:
         eng.close()
         if world > 1:
@@ -349,7 +367,7 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {"bound": "fp64", "achieved": fp_it * its_kernel / 1e9, "peak": fp64_peak / 1e9, "unit": "G FP64-instr/s",
-                "frac": fp_it * its_kernel / fp64_peak, "traffic": None,
+                "frac": fp_it * its_kernel / fp64_peak, "traffic": ncu_traffic_bytes(),
                 "peak_source": "pwgs_fp64_peak: DFMA chains measured live on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
                 "algorithmic_fp64_instr_per_iteration": fp_it, "kernel_ms_per_launch": kms,
                 "cnv_ssm_by_merged_states": stats[:3], "cnv_entry_states": stats[3],
