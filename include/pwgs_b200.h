@@ -110,7 +110,9 @@ int pwgs_get_lbc(pwgs_ctx *ctx, double *out /* [D*T] log_bin_coeff(d,a), mh.cpp:
 int pwgs_get_data_states(pwgs_ctx *ctx, int32_t *M, int32_t *ssm_of_m, int32_t *coef);
 
 /* Tuning knobs: "mh_batch" (largest speculative batch of proposals per grid barrier: a power of two in 1..128 = default; the kernel
- * adapts the actual batch to the running acceptance rate) and "mh_ctas" (CTAs per chain, 0 = all SMs). */
+ * adapts the actual batch to the running acceptance rate), "mh_ctas" (CTAs per chain, 0 = all SMs) and "mh_collapse" (1: plain
+ * data enter the MH likelihood through exact integer totals per (node, error-rate class, sample) instead of one term per datum;
+ * off by default, available when the data have at most 16 distinct (mu_r, mu_v) pairs). */
 int pwgs_set_option(pwgs_ctx *ctx, const char *name, int64_t value);
 int pwgs_get_option(pwgs_ctx *ctx, const char *name, int64_t *value);
 

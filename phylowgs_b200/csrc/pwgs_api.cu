@@ -52,6 +52,11 @@ struct pwgs_ctx {
     DevBuf<double> mu_r, mu_v, lbc;
     DevBuf<int> pidx, pa, pd, pnode, cidx, ca, cd;        // permuted work lists (plain first / CNV-affected SSMs)
     DevBuf<double> pmu_r, pmu_v, cmu_r, clbc;
+    // error-rate classes of the plain data (opt-in sufficient-statistics path, K0d)
+    int n_classes = 0, opt_collapse = 0;
+    DevBuf<int> pcls;
+    DevBuf<double> cl_mu_r, cl_mu_v;
+    DevBuf<unsigned long long> cl_sums;
     double lbc_plain_sum = 0;
     // ---- tree
     bool tree_set = false;
@@ -123,6 +128,7 @@ int pwgs_destroy(pwgs_ctx *c)
     c->mu_r.release(); c->mu_v.release(); c->lbc.release();
     c->pidx.release(); c->pa.release(); c->pd.release(); c->pnode.release(); c->cidx.release(); c->ca.release(); c->cd.release();
     c->pmu_r.release(); c->pmu_v.release(); c->cmu_r.release(); c->clbc.release();
+    c->pcls.release(); c->cl_mu_r.release(); c->cl_mu_v.release(); c->cl_sums.release();
     c->parent.release(); c->depth.release(); c->tin.release(); c->tout.release(); c->order.release(); c->node_of_datum.release();
     c->phi.release(); c->pi.release(); c->coef.release();
     c->code_tmp.release(); c->enode_tmp.release(); c->pos.release(); c->w_a.release(); c->w_d.release(); c->w_code.release();
@@ -224,6 +230,24 @@ int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
         int j = c->ssm_of_m[m];
         cmr[m] = mu_r[j];
         for (int tp = 0; tp < T; tp++) { ca[(size_t)tp * M + m] = a[(size_t)j * T + tp]; cd[(size_t)tp * M + m] = d[(size_t)j * T + tp]; }
+    }
+    {   // distinct (mu_r, mu_v) pairs of the plain data; more than 16 classes disables the collapsed path
+        std::vector<int> pcls(std::max(Dp, 1), 0);
+        std::vector<double> cr, cv;
+        bool ok = true;
+        for (int i = 0; i < Dp && ok; i++) {
+            int f = -1;
+            for (size_t q = 0; q < cr.size(); q++) if (cr[q] == pmr[i] && cv[q] == pmv[i]) { f = (int)q; break; }
+            if (f < 0) { if (cr.size() >= 16) { ok = false; break; } cr.push_back(pmr[i]); cv.push_back(pmv[i]); f = (int)cr.size() - 1; }
+            pcls[i] = f;
+        }
+        c->n_classes = ok ? (int)cr.size() : 0;
+        if (c->n_classes > 0) {
+            CREATE_TRY(c->pcls.upload(pcls.data(), Dp, s));
+            CREATE_TRY(c->cl_mu_r.upload(cr.data(), cr.size(), s));
+            CREATE_TRY(c->cl_mu_v.upload(cv.data(), cv.size(), s));
+            CREATE_TRY(cudaStreamSynchronize(s));
+        }
     }
     CREATE_TRY(c->pidx.upload(pidx.data(), Dp, s));
     CREATE_TRY(c->pa.upload(pa.data(), (size_t)Dp * T, s));
@@ -395,8 +419,18 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->abort_flag.p, 0, sizeof(int), c->stream));
 
+    const int collapse = (c->opt_collapse && c->n_classes > 0 && c->Dp > 0) ? c->n_classes : 0;
+    if (collapse) {
+        const size_t n = (size_t)c->K * collapse * c->T * 2;
+        CUDA_TRY(c->cl_sums.alloc(n));
+        CUDA_TRY(cudaMemsetAsync(c->cl_sums.p, 0, n * sizeof(unsigned long long), c->stream));
+        collapse_kernel<<<(c->Dp + 255) / 256, 256, 0, c->stream>>>(c->Dp, c->T, collapse, c->pa.p, c->pd.p, c->pnode.p, c->pcls.p, c->cl_sums.p);
+        CUDA_TRY(cudaGetLastError());
+        c->n_launches++;
+    }
     MhParams p;
     p.Dp = c->Dp; p.M = c->M; p.T = c->T; p.K = c->K;
+    p.n_classes = collapse; p.cl_sums = c->cl_sums.p; p.cl_mu_r = c->cl_mu_r.p; p.cl_mu_v = c->cl_mu_v.p;
     p.pa = c->pa.p; p.pd = c->pd.p; p.pmu_r = c->pmu_r.p; p.pmu_v = c->pmu_v.p; p.pnode = c->pnode.p;
     p.cw = c->work;
     p.tin = c->tin.p; p.tout = c->tout.p; p.phi0 = c->phi.p; p.pi0 = c->pi.p;
@@ -573,6 +607,8 @@ int pwgs_set_option(pwgs_ctx *c, const char *name, int64_t value)
     } else if (n == "mh_dist") {
         if (value < -1 || value > 1) return fail(PWGS_EINVAL, "mh_dist must be -1 (auto), 0 or 1");
         c->opt_dist = (int)value;
+    } else if (n == "mh_collapse") {
+        c->opt_collapse = value != 0;
     } else if (n == "mh_stage") {
         c->opt_stage = value != 0;
     } else if (n == "mh_profile") {
@@ -620,6 +656,8 @@ int pwgs_get_option(pwgs_ctx *c, const char *name, int64_t *value)
     else if (n == "n_plain") *value = c->Dp;
     else if (n == "n_cnv_ssm") *value = c->M;
     else if (n == "launches") *value = c->n_launches;
+    else if (n == "n_classes") *value = c->n_classes;
+    else if (n == "mh_collapse") *value = c->opt_collapse;
     else if (n.rfind("mh_prof_", 0) == 0 && n.size() == 9 && n[8] >= '0' && n[8] <= '9') *value = (int64_t)c->prof_host[n[8] - '0'];
     else if (n.rfind("mh_prof_1", 0) == 0 && n.size() == 10 && n[9] >= '0' && n[9] <= '5') *value = (int64_t)c->prof_host[10 + n[9] - '0'];
     else return fail(PWGS_EINVAL, "unknown option " + n);

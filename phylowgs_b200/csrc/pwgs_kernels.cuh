@@ -310,6 +310,25 @@ __global__ void sum_kernel(int n, const double *__restrict__ x, double *out)
     }
 }
 
+// ============================================================================ K0d  sufficient statistics of the plain data
+// With the assignments frozen during mh_loop, every plain datum in node k with error rates (mu_r, mu_v) of class c contributes
+// a*log(mu_kc) + (d-a)*log(1-mu_kc) with the SAME mu_kc: the sum over those data is A_kc*log(mu_kc) + B_kc*log(1-mu_kc) with the
+// integer totals A = sum a, B = sum (d-a) (exact in 64-bit integers).  Opt-in ("mh_collapse"): the general path streams
+// every datum, because the input format allows arbitrary per-SSM error rates (README.md:30-41); real inputs have <= 3 classes.
+__global__ void collapse_kernel(int Dp, int T, int C, const int *__restrict__ pa, const int *__restrict__ pd,
+                                const int *__restrict__ pnode, const int *__restrict__ pcls, unsigned long long *__restrict__ sums)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Dp) return;
+    const int k = pnode[i], c = pcls[i];
+    for (int tp = 0; tp < T; tp++) {
+        const int a = pa[(size_t)tp * Dp + i], d = pd[(size_t)tp * Dp + i];
+        unsigned long long *s = sums + 2 * (((size_t)k * C + c) * T + tp);
+        atomicAdd(s, (unsigned long long)a);                       // integer sums: exact and order-independent
+        atomicAdd(s + 1, (unsigned long long)(d - a));
+    }
+}
+
 // ============================================================================ K1
 #define MH_CWARPS 11                     // consumer warps (likelihood + bookkeeping); with the producer warp that is 12 warps = 3 per
                                          // SM sub-partition, the most that fit at 168 registers (8 interleaved chains of fp64 logarithms per thread)
@@ -327,6 +346,9 @@ struct MhParams {
     const double *pmu_r, *pmu_v;        // [Dp]
     const int *pnode;                   // [Dp] node index of each plain datum
     CnvWork cw;                         // CNV-affected SSMs: sorted, CTA-major sparse work list (K0c)
+    int n_classes;                      // > 0: plain data enter through their per-(node, class, sample) totals (K0d)
+    const unsigned long long *cl_sums;  // [K][n_classes][T][2] = {sum a, sum d-a}
+    const double *cl_mu_r, *cl_mu_v;    // [n_classes]
     const int *tin, *tout;              // [K] Euler-tour interval of every node (subtree test)
     const double *phi0, *pi0;           // [K*T] state on entry
     double *phi_out, *pi_out;           // [K*T] state on exit
@@ -558,7 +580,8 @@ __host__ __device__ inline size_t mh_stage_bytes(int pchunk, int cchunk, int T, 
 // the group's stride and accumulating BU sums, so that every load / int->fp64 conversion is shared by BU proposals and the BU
 // independent chains of logarithms overlap in the FP64 pipe.  Leaves red[bb][warp] = the warp's sum for proposal g*BU+bb.
 template <int BU, class Slice>
-__device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S, const Slice &sl, int cur, int wpg, int role, int g, int lane)
+__device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S, const Slice &sl, int cur, int wpg, int role, int g, int lane,
+                                              int rank, int cpc)
 {
     // proposal group g (proposals g*BU .. g*BU+BU-1) is evaluated by wpg warps; this warp is number `role` of them
     const int T = p.T, KT = p.K * T;
@@ -693,6 +716,27 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
             for (int bb = 0; bb < BU; bb++) acc[bb] += fa * ll[bb] + fb * ll[BU + bb];
         }
     }
+    // ---- plain data through their sufficient statistics (K0d): entry (node, class, sample) e belongs to CTA e mod cpc
+    if (p.n_classes > 0) {
+        const int C = p.n_classes, n_ent = p.K * C * T;
+#pragma unroll 1
+        for (int e = rank + cpc * lt; e - cpc * lane < n_ent; e += cpc * tpg) {
+            const bool act = e < n_ent;
+            const int ee = act ? e : 0, k = ee / (C * T), c = (ee / T) % C, tp = ee % T;
+            const double A = act ? (double)p.cl_sums[2 * ee] : 0.0, B = act ? (double)p.cl_sums[2 * ee + 1] : 0.0;
+            const double mu_r = p.cl_mu_r[c], mu_v = p.cl_mu_v[c];
+            double xx[2 * BU], ll[2 * BU];
+#pragma unroll
+            for (int bb = 0; bb < BU; bb++) {
+                const double phi = bphi[bb * KT + k * T + tp];
+                xx[bb] = (1.0 - phi) * mu_r + phi * mu_v;
+                xx[BU + bb] = 1.0 - xx[bb];
+            }
+            pwgs_log_pos_n<2 * BU>(xx, ll);
+#pragma unroll
+            for (int bb = 0; bb < BU; bb++) acc[bb] += A * ll[bb] + B * ll[BU + bb];
+        }
+    }
 #pragma unroll
     for (int bb = 0; bb < BU; bb++) {
         const double t = warp_sum(acc[bb]);
@@ -784,7 +828,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
     // this CTA's slices of the plain work list (contiguous) and of the CNV work list (already CTA-major)
     const int pchunk = (p.Dp + cpc - 1) / cpc, p0 = min(p.Dp, rank * pchunk), p1 = min(p.Dp, p0 + pchunk);
     const CnvWork &cw = p.cw;
-    const int cbase = rank * cw.cchunk, np = p1 - p0, nc = (p.M - rank + cpc - 1) / cpc;
+    const int cbase = rank * cw.cchunk, np = p.n_classes > 0 ? 0 : p1 - p0, nc = (p.M - rank + cpc - 1) / cpc;
     typename std::conditional<STAGED, SliceShared, SliceGlobal>::type sl;
     if constexpr (STAGED) {
         // carve the staging area behind the node tables (16-byte aligned) and copy the slice once
@@ -873,12 +917,12 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
             // sub-partitions (warp id % 4) in different groups
             if (warp < MH_GWARPS) {
                 const int gq = warp / wpg, role = (warp - gq * wpg + gq) % wpg;
-                if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, wpg, role, gq, lane); else mh_likelihood<1>(p, S, sl, cur, wpg, role, gq, lane);
+                if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, wpg, role, gq, lane, rank, cpc); else mh_likelihood<1>(p, S, sl, cur, wpg, role, gq, lane, rank, cpc);
             }
         } else {
 #pragma unroll 1
             for (int gq = warp; gq < ngroups; gq += MH_CWARPS)                  // large batches: several groups per warp, in turn
-                mh_likelihood<MH_BU>(p, S, sl, cur, 1, 0, gq, lane);
+                mh_likelihood<MH_BU>(p, S, sl, cur, 1, 0, gq, lane, rank, cpc);
         }
         consumer_sync();
         MH_PROF(0);

@@ -87,6 +87,11 @@ class GpuBackend(Backend):
         self.n_cnv = len(data) - self.n_ssm
         self.ntps = arr["a"].shape[1]
         self.engine = Engine(device=device, **arr)
+        # plain data through exact integer totals per (node, error-rate class, sample) in the MH kernel (K0d); PWGS_MH_COLLAPSE=0
+        # keeps the per-datum streaming path
+        import os
+        if os.environ.get("PWGS_MH_COLLAPSE", "1") != "0" and self.engine.get_option("n_classes") > 0:
+            self.engine.set_option("mh_collapse", 1)
 
     def set_tree_arrays(self, parent, node_of_datum, phi, pi):
         self.engine.set_tree(parent, node_of_datum, phi, pi)

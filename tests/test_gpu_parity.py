@@ -114,3 +114,21 @@ def test_mh_bundled_example_matches_oracle(oracle, gpu_lib):
     assert got["ratio"] * 500 == want["accepted"]
     assert rel(got["pi"], want["pi"]) < 1e-9
     assert rel(got["llh"], want["llh"]) < RTOL
+
+
+@pytest.mark.parametrize("ctas", [1, 0])
+def test_mh_collapsed_plain_data_walks_the_same_chain(oracle, gpu_lib, ctas):
+    """Opt-in sufficient statistics (mh_collapse): exact integer totals per (node, class, sample) replace the per-datum terms
+    of the plain data; only the order of fp64 additions changes, so the chain must still be the oracle's."""
+    data, tree = cases.synthetic_case(oracle, n_ssm=400, n_cnv=10, T=2, K=7, seed=21)
+    iters, std, seed, stream = 300, 1000.0, 1234, 7
+    want = oracle.mh_loop(data, tree, iters, std, oracle.RNG_PHILOX, seed, stream)
+    with cases.engine_for(gpu_lib, data, tree) as eng:
+        assert eng.get_option("n_classes") >= 1
+        eng.set_option("mh_collapse", 1)
+        eng.set_option("mh_ctas", ctas)
+        assert rel(eng.total_llh(gpu_lib.SEM_MH), oracle.multi_param_post(data, tree)) < RTOL
+        got = eng.mh_run(iters, std, seed, stream)
+    assert got["ratio"] * iters == want["accepted"]
+    assert rel(got["pi"], want["pi"]) < 1e-9
+    assert rel(got["llh"], want["llh"]) < RTOL
