@@ -153,15 +153,10 @@ __device__ __forceinline__ void pwgs_log_pos_n(const double (&x)[N], double (&r)
     double f[N], d[N], y[N], t[N], q[N], z[N], w[N], t1[N], t2[N], dk[N], hf[N];
 #pragma unroll
     for (int i = 0; i < N; i++) {
-        int hi = __double2hiint(x[i]);
-        const int lo = __double2loint(x[i]);
-        int e = (hi >> 20) - 1023;
-        hi &= 0x000fffff;
-        const int k = (hi + 0x95f64) & 0x100000;
-        hi |= k ^ 0x3ff00000;
-        e += k >> 20;
-        dk[i] = (double)e;
-        f[i] = __hiloint2double(hi, lo) - 1.0;
+        // x = 2^e * m with m in [sqrt(2)/2, sqrt(2)): shift the high word so that the exponent field changes exactly at sqrt(2)
+        const int hs = __double2hiint(x[i]) + (0x3ff00000 - 0x3fe6a09e);
+        dk[i] = (double)((hs >> 20) - 1023);
+        f[i] = __hiloint2double((hs & 0x000fffff) + 0x3fe6a09e, __double2loint(x[i])) - 1.0;
     }
 #pragma unroll
     for (int i = 0; i < N; i++) d[i] = 2.0 + f[i];
