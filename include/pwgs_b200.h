@@ -121,6 +121,46 @@ int pwgs_get_option(pwgs_ctx *ctx, const char *name, int64_t *value);
  * library's kernels launched for the context so far. */
 int pwgs_get_stream(pwgs_ctx *ctx, void **stream);
 
+/* ---- host side of TSSB.resample_assignments (tssb.py:82-150 with find_node 340-377): the serial slice sampler over the unit
+ * interval, native, reading the datum x node log-likelihood grid from host memory (one column per node, filled from
+ * pwgs_llh_rows / pwgs_llh_block).  No device work happens inside; the callbacks let the caller mirror tree edits and fetch
+ * the grid entries an edit makes necessary.
+ *   nodes: preorder at entry (node 0 = root, parent[k] < k); spawned nodes get the next indices.  Children of node k and their
+ *   sticks: child_idx / child_stick[child_ptr[k] .. child_ptr[k+1]) in stick order.
+ *   uniforms: consumed strictly in this order - per datum one for the slice level (log u + llh), then per candidate one for
+ *   the point of the interval; inside find_node, per spawned child: stick (only below depth 0; Beta(1,dp_gamma) by inversion
+ *   1-u^(1/b)), the fraction of the parent's pi it takes (alleles.py:35), main (Beta(1, alpha_decay^(depth+1)*dp_alpha)).
+ *   refill() is called when the buffer runs out; it refills `uniforms` in place and returns how many it wrote.
+ *   on_spawn(user, n): called after find_node spawned nodes while datum n is being placed, before any column of a new node is
+ *   read: the callee mirrors spawn_*[already mirrored .. n_spawned) and stores the new nodes' columns in cols[].
+ *   on_cnv_move(user, n): CNV datum n moved (assignments[n] is already updated): refresh the rows of its SSMs that are still
+ *   to be visited.
+ * Returns 0, or a negative code (PWGS_EINVAL; -3 uniforms exhausted; -4 node / spawn capacity; -6/-7 callback failure). */
+typedef struct pwgs_sweep {
+    int32_t n_data, n_ssm;
+    int32_t n_nodes, cap_nodes;
+    const int32_t *parent;            /* [n_nodes] */
+    const double *main;               /* [n_nodes] */
+    const int32_t *child_ptr;         /* [n_nodes+1] */
+    const int32_t *child_idx;         /* [n_nodes-1] */
+    const double *child_stick;        /* [n_nodes-1] */
+    int32_t *assignments;             /* [n_data] node index per datum, in/out */
+    double **cols;                    /* [cap_nodes] cols[k][n] = llh of datum n in node k */
+    double *uniforms;
+    int32_t n_uniforms;
+    double dp_alpha, dp_gamma, alpha_decay;
+    int32_t min_depth, max_depth;
+    int32_t cap_spawn, n_spawned;     /* log of spawned nodes, in spawn order: node index = n_nodes + position */
+    int32_t *spawn_parent;
+    double *spawn_stick, *spawn_main, *spawn_frac;
+    void *user;
+    int (*on_spawn)(void *user, int32_t n);
+    int (*on_cnv_move)(void *user, int32_t n);
+    int (*refill)(void *user);
+    int32_t n_moved, n_shrunk, uniforms_used;   /* out */
+} pwgs_sweep;
+int pwgs_resample_assignments(pwgs_sweep *sweep);
+
 /* Measured FP64-pipe issue peak of the device (DFMA chains, thread-instructions/s) — the roofline
  * denominator for the MH kernel, which is FP64-pipe-bound, not HBM-bound. */
 int pwgs_fp64_peak(int device, double *dfma_per_s);

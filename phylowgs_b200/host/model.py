@@ -21,6 +21,12 @@ def boundbeta(rng, a, b):
     return (1.0 - EPS) * (rng.beta(a, b) - 0.5) + 0.5
 
 
+def boundbeta1(u, b):
+    """boundbeta(1, b) from one uniform by inversion (Beta(1,b): x = 1 - u^(1/b)); the form both the Python and the native
+    assignment sweep use, so that they consume the same stream of uniforms (csrc/pwgs_host_sampler.cpp)."""
+    return (1.0 - EPS) * ((1.0 - u ** (1.0 / b)) - 0.5) + 0.5
+
+
 def betapdfln(x, a, b):
     """log Beta(x; a, b) (util.py:26-27)."""
     return gammaln(a + b) - gammaln(a) - gammaln(b) + (a - 1.0) * np.log(x) + (b - 1.0) * np.log(1.0 - x)
@@ -102,8 +108,8 @@ class Node(object):
     def get_data(self):
         return [self.tssb.data[n] for n in self.data]
 
-    def spawn(self):
-        return self.__class__(parent=self, tssb=self.tssb)
+    def spawn(self, **kw):
+        return self.__class__(parent=self, tssb=self.tssb, **kw)
 
     def kill(self):
         if self._parent is not None:
@@ -120,7 +126,7 @@ class alleles(Node):
     min_conc = 0.01
     max_conc = 0.1
 
-    def __init__(self, parent=None, tssb=None, conc=0.1, ntps=5):
+    def __init__(self, parent=None, tssb=None, conc=0.1, ntps=5, frac=None):
         super(alleles, self).__init__(parent=parent, tssb=tssb)
         if tssb is not None:
             ntps = len(tssb.data[0].a)
@@ -133,7 +139,9 @@ class alleles(Node):
             self.pi = np.ones(ntps)
             self.params = np.ones(ntps)
         else:
-            frac = tssb.rng.rand(1) if tssb is not None else np.random.rand(1)
+            if frac is None:                                # the share of the parent's pi: one uniform for all samples
+                stream = getattr(tssb, "ustream", None)
+                frac = stream.next() if stream is not None else (tssb.rng.rand(1) if tssb is not None else np.random.rand(1))
             self.pi = frac * parent.pi
             parent.pi = parent.pi - self.pi
             self.params = self.pi
@@ -178,6 +186,7 @@ class TSSB(object):
         if root_node is None:
             raise Exception("Root node must be specified.")
         self.rng = rng if rng is not None else np.random.RandomState()
+        self.ustream = None                                 # set during an assignment sweep: the sweep's stream of uniforms
         self.backend = backend
         self.min_depth = min_depth
         self.max_depth = max_depth
@@ -196,23 +205,31 @@ class TSSB(object):
     # the generator and the device context are process-local: keep them out of trees.zip / state pickles
     def __getstate__(self):
         st = dict(self.__dict__)
-        st.pop("backend", None)
-        st.pop("rng", None)
+        for key in ("backend", "rng", "ustream", "_ssms_of_cnv"):
+            st.pop(key, None)
         return st
 
     def __setstate__(self, st):
         self.__dict__.update(st)
         self.backend = None
         self.rng = None
+        self.ustream = None
 
     # ------------------------------------------------------------------ traversal
     def _new_child(self, entry, depth):
         """Break a new stick under `entry` and spawn its node (tssb.py:353-361 / 220-225)."""
         self.n_spawned = getattr(self, "n_spawned", 0) + 1
-        stick = boundbeta(self.rng, 1, self.dp_gamma) if depth != 0 else 0.999
+        us = getattr(self, "ustream", None)
+        a_child = (float(self.alpha_decay) ** (depth + 1)) * float(self.dp_alpha)
+        if us is not None:                                  # inside a sweep: stick, share of pi, main, each from one uniform
+            stick = boundbeta1(us.next(), float(self.dp_gamma)) if depth != 0 else 0.999
+            node = entry["node"].spawn()
+            main = boundbeta1(us.next(), a_child) if self.min_depth <= depth + 1 else 0.0
+        else:
+            stick = boundbeta(self.rng, 1, self.dp_gamma) if depth != 0 else 0.999
+            node = entry["node"].spawn()
+            main = boundbeta(self.rng, 1.0, a_child) if self.min_depth <= depth + 1 else 0.0
         entry["sticks"] = np.vstack([entry["sticks"], stick])
-        node = entry["node"].spawn()
-        main = boundbeta(self.rng, 1.0, (self.alpha_decay ** (depth + 1)) * self.dp_alpha) if self.min_depth <= depth + 1 else 0.0
         entry["children"].append(_entry(node, main))
 
     def find_node(self, u):

@@ -3,18 +3,47 @@
 * `resample_assignments` (tssb.py:82-150): the slice sampler over the unit interval is inherently sequential (each datum's
   move changes node occupancy, and `find_node` may spawn nodes), but the only expensive thing it asks for is
   "log-likelihood of datum n if it sat in node k".  The reference answers that with one Python `logprob` call that re-derives
-  tree metadata every time (O(N + K) each, O(N^2) per sweep, data.py:33-38).  Here the whole datum x node grid comes from ONE
-  device call per tree version (pwgs_llh_rows, Python convention of data.py); it is refreshed only when the tree changes in a
-  way that can change unread rows: a node was spawned (new column, and the parent's pi moved), or a CNV datum moved (its SSMs'
-  rows).  Decisions compare fp64 numbers produced by the device against host-drawn uniforms, so given the same uniforms the
-  assignment indices are those of the CPU oracle.
+  tree metadata every time (O(N + K) each, O(N^2) per sweep, data.py:33-38).  Here the datum x node grid comes from the device
+  (pwgs_llh_rows once per sweep, pwgs_llh_block for what a tree edit makes necessary, see `_Grid`), and the serial loop itself
+  runs natively in the library (pwgs_resample_assignments, csrc/pwgs_host_sampler.cpp) with the tree edits mirrored back here.
+  `resample_assignments_py` is the same sweep in Python; both consume one stream of uniforms in the same order and are
+  bit-for-bit interchangeable (tests/test_host_chain.py), which is also what the CPU-oracle chain of the parity tests runs.
+  Decisions compare fp64 numbers produced by the device against host-drawn uniforms, so given the same uniforms the assignment
+  indices are those of the CPU oracle.
 * `complete_data_log_likelihood` (tssb.py:404-410): sum_k n_k log w_k on the host + one device reduction for the data term.
 """
+import ctypes as C
+import math
+import os
 import sys
 
 import numpy as np
 
 from .model import EPS
+
+
+class UniformStream(object):
+    """Block-buffered uniforms from the chain's generator: the only randomness a sweep consumes (Beta(1,b) draws are taken by
+    inversion, model.boundbeta1), in the order documented at pwgs_resample_assignments (include/pwgs_b200.h)."""
+
+    def __init__(self, rng, block):
+        self.rng = rng
+        self.buf = rng.rand(block)
+        self.pos = 0
+        self.n = block
+
+    def refill(self):
+        self.buf[:] = self.rng.rand(len(self.buf))
+        self.pos = 0
+        self.n = len(self.buf)
+        return self.n
+
+    def next(self):
+        if self.pos >= self.n:
+            self.refill()
+        v = self.buf[self.pos]
+        self.pos += 1
+        return float(v)
 
 
 def _path_cmp(cur, new):
@@ -32,7 +61,7 @@ def _path_cmp(cur, new):
 
 
 class _Grid(object):
-    """llh[n, k]: log-likelihood of datum n if it sat in node k, filled by device calls and kept valid through the sweep.
+    """cols[k][n]: log-likelihood of datum n if it sat in node k, filled by device calls and kept valid through the sweep.
 
     Nodes get stable indices for the sweep: preorder position at the start, then spawn order (pwgs_set_tree takes any node
     order), so columns never move.  What invalidates entries that are still to be read:
@@ -48,6 +77,13 @@ class _Grid(object):
         self.backend = b = t.backend
         self.nodes = list(b.sync_tree(t))                   # preorder; the device tree now equals the host tree
         self.uid = {id(nd): k for k, nd in enumerate(self.nodes)}
+        self.entries = []                                   # tree entry dict of every node, same indexing
+        stack = [t.root]
+        while stack:
+            e = stack.pop()
+            self.entries.append(e)
+            stack.extend(reversed(e["children"]))
+        assert all(e["node"] is nd for e, nd in zip(self.entries, self.nodes))
         self.nod = np.zeros(t.num_data, dtype=np.int32)
         for k, nd in enumerate(self.nodes):
             if nd.data:
@@ -55,8 +91,7 @@ class _Grid(object):
         self.spawned = getattr(t, "n_spawned", 0)
         self.calls = 1
         full = b.llh_rows(np.arange(t.num_data, dtype=np.int32))
-        self.llh = np.empty((t.num_data, max(2 * full.shape[1], 32)))
-        self.llh[:, :full.shape[1]] = full
+        self.cols = [np.ascontiguousarray(full[:, k]) for k in range(full.shape[1])]
         if not hasattr(t, "_ssms_of_cnv"):                  # CNV datum index -> SSM datum indices linked to it
             m = {}
             for d in t.data:
@@ -71,22 +106,34 @@ class _Grid(object):
         pi = np.array([np.asarray(nd.pi, dtype=np.float64).reshape(-1) for nd in nodes])
         self.backend.set_tree_arrays(parent, self.nod, phi, pi)
 
-    def after_spawn(self, n):
-        """Columns of the nodes spawned since the last look, for the data still to be visited."""
-        new = [nd for nd in self.tssb.get_nodes() if id(nd) not in self.uid]
-        first = len(self.nodes)
-        for nd in new:
-            self.uid[id(nd)] = len(self.nodes)
-            self.nodes.append(nd)
-        if len(self.nodes) > self.llh.shape[1]:
-            grown = np.empty((self.llh.shape[0], 2 * len(self.nodes)))
-            grown[:, :first] = self.llh[:, :first]
-            self.llh = grown
+    def register(self, entry):
+        """A node spawned during the sweep gets the next index."""
+        self.uid[id(entry["node"])] = len(self.nodes)
+        self.nodes.append(entry["node"])
+        self.entries.append(entry)
+
+    def fetch_new_columns(self, n, first):
+        """Columns of nodes[first:] for the data still to be visited (rows n..)."""
         self._push_tree()
         cols = np.arange(first, len(self.nodes), dtype=np.int32)
-        self.llh[n:, first:len(self.nodes)] = self.backend.llh_block(np.arange(n, self.tssb.num_data, dtype=np.int32), cols)
+        block = self.backend.llh_block(np.arange(n, self.tssb.num_data, dtype=np.int32), cols)
+        for i in range(len(cols)):
+            col = np.empty(self.tssb.num_data)
+            col[n:] = block[:, i]
+            self.cols.append(col)
         self.spawned = getattr(self.tssb, "n_spawned", 0)
         self.calls += 1
+
+    def after_spawn_py(self, n):
+        first = len(self.nodes)
+        known = self.uid
+        stack = [self.tssb.root]
+        while stack:                                        # preorder walk: spawn order within one find_node call is top-down
+            e = stack.pop()
+            if id(e["node"]) not in known:
+                self.register(e)
+            stack.extend(reversed(e["children"]))
+        self.fetch_new_columns(n, first)
 
     def after_cnv_move(self, n, cnv_index):
         rows = self.tssb._ssms_of_cnv.get(cnv_index)
@@ -97,57 +144,192 @@ class _Grid(object):
             return
         self._push_tree()
         K = len(self.nodes)
-        self.llh[rows, :K] = self.backend.llh_block(rows, np.arange(K, dtype=np.int32))
+        block = self.backend.llh_block(rows, np.arange(K, dtype=np.int32))
+        for k in range(K):
+            self.cols[k][rows] = block[:, k]
         self.calls += 1
 
     def get(self, n, node):
-        return self.llh[n, self.uid[id(node)]]
+        return self.cols[self.uid[id(node)]][n]
+
+
+def _uniform_block(tssb):
+    return 4 * tssb.num_data + 4096
+
+
+def resample_assignments_py(tssb):
+    """The sweep in Python (reference semantics tssb.py:82-150); consumes tssb.ustream like the native sweep does."""
+    root_entry = tssb.root
+    grid = _Grid(tssb)
+    stream = tssb.ustream = UniformStream(tssb.rng, _uniform_block(tssb))
+    n_ssm = tssb.backend.n_ssm
+    paths = {}
+    try:
+        for n in range(tssb.num_data):
+            datum = tssb.data[n]
+            cur = tssb.assignments[n]
+            indices = paths.get(id(cur))
+            if indices is None:                             # child-index path of the node (tssb.py:101-107); spawns append
+                indices, entry = [], root_entry             # children at the end, so paths stay valid through the sweep
+                for anc in cur.get_ancestors()[1:]:
+                    k = next(i for i, c in enumerate(entry["children"]) if c["node"] is anc)
+                    indices.append(k)
+                    entry = entry["children"][k]
+                paths[id(cur)] = indices
+            lo, hi = 0.0, 1.0
+            llh_s = math.log(stream.next()) + grid.get(n, cur)
+            while True:
+                u = (hi - lo) * stream.next() + lo
+                cand, path = tssb.find_node(u)
+                if cand.parent() is None:                   # keep the root empty (tssb.py:118-120)
+                    cand = cand.children()[0]
+                    path = [0]
+                if getattr(tssb, "n_spawned", 0) != grid.spawned:
+                    grid.after_spawn_py(n)
+                if grid.get(n, cand) > llh_s:
+                    if cand is not cur:
+                        cur.remove_datum(n)
+                        cand.add_datum(n)
+                        tssb.assignments[n] = cand
+                        datum.node = cand
+                        grid.nod[n] = grid.uid[id(cand)]
+                        if datum.index >= n_ssm:
+                            grid.after_cnv_move(n, datum.index)
+                    break
+                if abs(hi - lo) < EPS:
+                    sys.stderr.write("Slice sampler shrank down.  Keep current state.\n")
+                    break
+                if _path_cmp(indices, path) < 0:
+                    lo = u
+                else:
+                    hi = u
+    finally:
+        tssb.ustream = None
+    tssb.last_grid_refreshes = grid.calls
+
+
+# ------------------------------------------------------------------ native sweep (libpwgs_b200.so, host code)
+_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32)
+_CB0 = C.CFUNCTYPE(C.c_int, C.c_void_p)
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class _Sweep(C.Structure):
+    _fields_ = [("n_data", C.c_int32), ("n_ssm", C.c_int32), ("n_nodes", C.c_int32), ("cap_nodes", C.c_int32),
+                ("parent", _ip), ("main", _dp), ("child_ptr", _ip), ("child_idx", _ip), ("child_stick", _dp),
+                ("assignments", _ip), ("cols", C.POINTER(_dp)), ("uniforms", _dp), ("n_uniforms", C.c_int32),
+                ("dp_alpha", C.c_double), ("dp_gamma", C.c_double), ("alpha_decay", C.c_double),
+                ("min_depth", C.c_int32), ("max_depth", C.c_int32), ("cap_spawn", C.c_int32), ("n_spawned", C.c_int32),
+                ("spawn_parent", _ip), ("spawn_stick", _dp), ("spawn_main", _dp), ("spawn_frac", _dp),
+                ("user", C.c_void_p), ("on_spawn", _CB), ("on_cnv_move", _CB), ("refill", _CB0),
+                ("n_moved", C.c_int32), ("n_shrunk", C.c_int32), ("uniforms_used", C.c_int32)]
+
+
+def resample_assignments_native(tssb):
+    from .. import _lib
+    from .model import _entry
+    lib = _lib.load()
+    grid = _Grid(tssb)
+    N, K0 = tssb.num_data, len(grid.nodes)
+    cap_nodes, cap_spawn = K0 + 8192, 8192
+    stream = UniformStream(tssb.rng, _uniform_block(tssb))
+
+    parent = np.array([-1 if nd.parent() is None else grid.uid[id(nd.parent())] for nd in grid.nodes], dtype=np.int32)
+    main = np.array([e["main"] for e in grid.entries], dtype=np.float64)
+    child_ptr = np.zeros(K0 + 1, dtype=np.int32)
+    child_idx, child_stick = [], []
+    for k, e in enumerate(grid.entries):
+        for i, c in enumerate(e["children"]):
+            child_idx.append(grid.uid[id(c["node"])])
+            child_stick.append(float(np.ravel(e["sticks"][i])[0]))
+        child_ptr[k + 1] = len(child_idx)
+    child_idx = np.array(child_idx if child_idx else [0], dtype=np.int32)
+    child_stick = np.array(child_stick if child_stick else [0.0], dtype=np.float64)
+    assign = grid.nod.copy()
+    before = assign.copy()
+    cols = (_dp * cap_nodes)()
+    for k, col in enumerate(grid.cols):
+        cols[k] = col.ctypes.data_as(_dp)
+    sp_parent = np.zeros(cap_spawn, dtype=np.int32)
+    sp_stick, sp_main, sp_frac = np.zeros(cap_spawn), np.zeros(cap_spawn), np.zeros(cap_spawn)
+    failure = []
+    state = {"mirrored": 0}
+    sw = _Sweep()
+
+    def mirror_spawns():
+        """Create the Python twins of the nodes the native sweep spawned since the last call (alleles.py:35-37, tssb.py:353-361)."""
+        for i in range(state["mirrored"], sw.n_spawned):
+            pe = grid.entries[int(sp_parent[i])]
+            pe["sticks"] = np.vstack([pe["sticks"], float(sp_stick[i])])
+            child = _entry(pe["node"].spawn(frac=float(sp_frac[i])), float(sp_main[i]))
+            pe["children"].append(child)
+            tssb.n_spawned = getattr(tssb, "n_spawned", 0) + 1
+            grid.register(child)
+        state["mirrored"] = sw.n_spawned
+
+    def on_spawn(_user, n):
+        try:
+            first = len(grid.nodes)
+            mirror_spawns()
+            grid.fetch_new_columns(int(n), first)
+            for k in range(first, len(grid.nodes)):
+                cols[k] = grid.cols[k].ctypes.data_as(_dp)
+            return 0
+        except BaseException as e:          # noqa: B902 - must not propagate through the C frame
+            failure.append(e)
+            return -1
+
+    def on_cnv_move(_user, n):
+        try:
+            grid.nod[:] = assign                            # the device needs the CNV's new node (and may as well get the rest)
+            grid.after_cnv_move(int(n), int(n))
+            return 0
+        except BaseException as e:          # noqa: B902
+            failure.append(e)
+            return -1
+
+    def refill(_user):
+        try:
+            return stream.refill()
+        except BaseException as e:          # noqa: B902
+            failure.append(e)
+            return 0
+
+    cb_spawn, cb_cnv, cb_refill = _CB(on_spawn), _CB(on_cnv_move), _CB0(refill)
+    sw.n_data, sw.n_ssm, sw.n_nodes, sw.cap_nodes = N, tssb.backend.n_ssm, K0, cap_nodes
+    sw.parent, sw.main = parent.ctypes.data_as(_ip), main.ctypes.data_as(_dp)
+    sw.child_ptr, sw.child_idx, sw.child_stick = child_ptr.ctypes.data_as(_ip), child_idx.ctypes.data_as(_ip), child_stick.ctypes.data_as(_dp)
+    sw.assignments, sw.cols = assign.ctypes.data_as(_ip), cols
+    sw.uniforms, sw.n_uniforms = stream.buf.ctypes.data_as(_dp), stream.n
+    sw.dp_alpha, sw.dp_gamma, sw.alpha_decay = tssb.dp_alpha, tssb.dp_gamma, tssb.alpha_decay
+    sw.min_depth, sw.max_depth = tssb.min_depth, tssb.max_depth
+    sw.cap_spawn, sw.n_spawned = cap_spawn, 0
+    sw.spawn_parent, sw.spawn_stick = sp_parent.ctypes.data_as(_ip), sp_stick.ctypes.data_as(_dp)
+    sw.spawn_main, sw.spawn_frac = sp_main.ctypes.data_as(_dp), sp_frac.ctypes.data_as(_dp)
+    sw.user, sw.on_spawn, sw.on_cnv_move, sw.refill = None, cb_spawn, cb_cnv, cb_refill
+    rc = lib.pwgs_resample_assignments(C.cast(C.byref(sw), C.c_void_p))
+    if failure:
+        raise failure[0]
+    if rc != 0:
+        raise RuntimeError("pwgs_resample_assignments failed with code %d" % rc)
+    mirror_spawns()
+    for _ in range(sw.n_shrunk):
+        sys.stderr.write("Slice sampler shrank down.  Keep current state.\n")
+    for n in np.nonzero(assign != before)[0]:
+        n = int(n)
+        old, new = grid.nodes[before[n]], grid.nodes[assign[n]]
+        old.remove_datum(n)
+        new.add_datum(n)
+        tssb.assignments[n] = new
+        tssb.data[n].node = new
+    tssb.last_grid_refreshes = grid.calls
 
 
 def resample_assignments(tssb):
-    rng, root_entry = tssb.rng, tssb.root
-    grid = _Grid(tssb)
-    n_ssm = tssb.backend.n_ssm
-    paths = {}
-    for n in range(tssb.num_data):
-        datum = tssb.data[n]
-        cur = tssb.assignments[n]
-        indices = paths.get(id(cur))
-        if indices is None:                                 # child-index path of the node (tssb.py:101-107); spawns append
-            indices, entry = [], root_entry                 # children at the end, so paths stay valid through the sweep
-            for anc in cur.get_ancestors()[1:]:
-                k = next(i for i, c in enumerate(entry["children"]) if c["node"] is anc)
-                indices.append(k)
-                entry = entry["children"][k]
-            paths[id(cur)] = indices
-        lo, hi = 0.0, 1.0
-        llh_s = np.log(rng.rand()) + grid.get(n, cur)
-        while True:
-            u = (hi - lo) * rng.rand() + lo
-            cand, path = tssb.find_node(u)
-            if cand.parent() is None:                       # keep the root empty (tssb.py:118-120)
-                cand = cand.children()[0]
-                path = [0]
-            if getattr(tssb, "n_spawned", 0) != grid.spawned:
-                grid.after_spawn(n)
-            if grid.get(n, cand) > llh_s:
-                if cand is not cur:
-                    cur.remove_datum(n)
-                    cand.add_datum(n)
-                    tssb.assignments[n] = cand
-                    datum.node = cand
-                    grid.nod[n] = grid.uid[id(cand)]
-                    if datum.index >= n_ssm:
-                        grid.after_cnv_move(n, datum.index)
-                break
-            if abs(hi - lo) < EPS:
-                sys.stderr.write("Slice sampler shrank down.  Keep current state.\n")
-                break
-            if _path_cmp(indices, path) < 0:
-                lo = u
-            else:
-                hi = u
-    tssb.last_grid_refreshes = grid.calls
+    if os.environ.get("PWGS_PY_SAMPLER", "0") == "1":
+        return resample_assignments_py(tssb)
+    return resample_assignments_native(tssb)
 
 
 def complete_data_log_likelihood(tssb):

@@ -87,3 +87,29 @@ def test_tree_pickles_use_reference_module_names(tmp_path):
     nd = back.get_nodes()[1]
     for attr in ("data", "_children", "_parent", "tssb", "params", "pi", "params1", "pi1", "path", "ht", "id"):
         assert hasattr(nd, attr), attr
+
+
+@pytest.mark.parametrize("files", ["bundled", "sim"])
+def test_native_sweep_equals_python_sweep(monkeypatch, tmp_path, files):
+    """pwgs_resample_assignments (native host code in the library) and sampler.resample_assignments_py consume the same stream
+    of uniforms in the same order: the chains they drive must be identical, spawned nodes, sticks and all."""
+    if files == "bundled":
+        ssm, cnv = SSM, CNV
+    else:
+        ssm = os.path.join(cases.GOLDEN, "emptysim.4.100.50.ssm.txt")
+        cnv = os.path.join(str(tmp_path), "empty.txt")
+        open(cnv, "w").close()
+    recs, trees = [], []
+    for py in ("1", "0"):
+        monkeypatch.setenv("PWGS_PY_SAMPLER", py)
+        tssb, n_ssms, n_cnvs = chain_util.new_chain(ssm, cnv, OracleBackend, seed=23)
+        recs.append(chain_util.run_chain(tssb, n_ssms, n_cnvs, iterations=7, mh_iters=150, seed=23))
+        trees.append(tssb)
+        check_invariants(tssb)
+    for a, b in zip(*recs):
+        assert np.array_equal(a["assign"], b["assign"])
+        assert a["n_nodes"] == b["n_nodes"] and a["llh"] == b["llh"] and a["hypers"] == b["hypers"]
+        assert np.array_equal(a["phi"], b["phi"])
+    wa, na = trees[0].get_mixture()
+    wb, nb = trees[1].get_mixture()
+    assert wa == wb and [sorted(n.data) for n in na] == [sorted(n.data) for n in nb]
