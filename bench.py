@@ -200,6 +200,60 @@ def ncu_traffic_bytes():
     return best
 
 
+def tree_sample_rate(s, device, iterations=6):
+    """Secondary figure of BASELINE's metric: full MCMC tree samples/s of one chain through the host glue (evolve.py:148-230:
+    assignment sweep + MH + sticks/hypers + LLH trace + pickling) on the same workload, the first iteration discarded.  The
+    reference's Python-2 side cannot run here, so there is no CPU number beside it (its sweep is O(N^2))."""
+    import pickle
+    from oracle import oracle as O                     # only to write the workload in the reference's file formats
+    from phylowgs_b200.host import evolve as E
+    from phylowgs_b200.host.backend import GpuBackend
+    from phylowgs_b200.host.model import TSSB, alleles, boundbeta
+    from phylowgs_b200.host.params import metropolis
+    with tempfile.TemporaryDirectory() as wd:
+        data = O.Data(s["a"], s["d"], s["mu_r"], s["mu_v"], s["n_ssm"], s["cnv_ptr"], s["cnv_idx"], s["cnv_c1"], s["cnv_c2"])
+        ssm, cnv = os.path.join(wd, "ssm_data.txt"), os.path.join(wd, "cnv_data.txt")
+        O.write_ssm_cnv(data, ssm, cnv)
+        codes, n_ssms, n_cnvs, _ = E.load_data(ssm, cnv)
+    E.install_pickle_aliases()
+    rng = np.random.RandomState(1)
+    backend = GpuBackend(codes, device=device)
+    root = alleles(conc=0.1, ntps=len(codes[0].a))
+    tssb = TSSB(dp_alpha=25.0, dp_gamma=1.0, alpha_decay=0.25, root_node=root, data=codes, rng=rng, backend=backend)
+    tssb.root["sticks"] = np.vstack([tssb.root["sticks"], .999999])
+    child = root.spawn()
+    tssb.root["children"].append({"node": child, "main": boundbeta(rng, 1.0, tssb.alpha_decay * tssb.dp_alpha),
+                                  "sticks": np.empty((0, 1)), "children": []})
+    for n in range(tssb.num_data):
+        root.remove_datum(n)
+        child.add_datum(n)
+        tssb.assignments[n] = child
+    for d in codes:
+        d.tssb = tssb
+    mh_std, times, parts = MH_STD, [], []
+    for it in range(iterations):
+        t = [time.perf_counter()]
+        tssb.resample_assignments(); t.append(time.perf_counter())
+        tssb.cull_tree()
+        acc = float(metropolis(tssb, MH_ITR, mh_std, 0, n_ssms, n_cnvs, "", "", 1, 1, ".", stream=it)); t.append(time.perf_counter())
+        if acc < 0.08 and mh_std < 10000:
+            mh_std *= 2.0
+        if 0.5 < acc < 0.99:
+            mh_std /= 2.0
+        tssb.resample_sticks(); tssb.resample_stick_orders(); tssb.resample_hypers()
+        tssb.complete_data_log_likelihood(); t.append(time.perf_counter())
+        pickle.dumps(tssb, protocol=2); t.append(time.perf_counter())
+        times.append(t[-1] - t[0])
+        parts.append(np.diff(t))
+    backend.close()
+    med = statistics.median(times[1:])
+    p = np.median(np.array(parts[1:]), axis=0)
+    return {"value": 1.0 / med, "unit": "tree samples/s", "iterations": iterations - 1, "mh_iterations_per_sample": MH_ITR,
+            "seconds": {"assignment_sweep": float(p[0]), "metropolis": float(p[1]), "sticks_hypers_llh": float(p[2]), "pickle": float(p[3])},
+            "note": "burn-in iterations from the one-node start (many spawned nodes); no CPU figure: the reference's Python-2 "
+                    "sweep cannot run here"}
+
+
 def reduce_max_over_ranks(x, world, device):
     """Every multi-GPU time is the MAX over ranks (one chain per rank; the job is as slow as its slowest chain)."""
     if world == 1:
@@ -371,6 +425,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return 0
+    tree_samples = tree_sample_rate(s, local_rank) if (world == 1 and not args.no_cpu_baseline) else None
 
     # ---- roofline of the dominant kernel (mh_kernel), per launch
     its_kernel = MH_ITR / (kms * 1e-3)
@@ -403,7 +458,8 @@ def main():
                                                  mh_batch=eng.get_option("mh_batch")),
             "accept_ratio": statistics.mean(ratios), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "collapsed_plain_data": collapsed}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "collapsed_plain_data": collapsed,
+            "tree_samples": tree_samples}
     print(json.dumps(line))
     eng.close()
     if world > 1:
