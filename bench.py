@@ -294,7 +294,7 @@ def main():
     K = len(s["parent"])
     by_it, _, D, M, T = algorithmic_work(s, K)
     config = {"workload": wl_desc, "n_ssm": int(s["n_ssm"]), "n_cnv": int(D - s["n_ssm"]), "n_cnv_affected_ssm": M, "ntps": T,
-              "tree_nodes": K, "mh_iterations_per_step": MH_ITR, "mh_std": mh_std, "chains": n_gpus, "parallelism": "1 chain per GPU, no collective"}
+              "tree_nodes": K, "mh_iterations_per_step": MH_ITR, "mh_std": mh_std, "chains": n_gpus, "parallelism": "1 chain per GPU, no collective (timing barrier over gloo)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -327,7 +327,10 @@ def main():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # The chains share nothing: there is no data-path collective, only the timing barrier and the max-over-ranks of the
+        # measured times.  Those are host-side scalars, so the process group is gloo over 127.0.0.1 (no NCCL communicator to set
+        # up, and nothing but the JSON line on stdout).
+        dist.init_process_group("gloo")
     dev = torch.device("cuda", local_rank)
 
     def barrier():
@@ -336,7 +339,7 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        return reduce_max_over_ranks(x, world, dev)
+        return reduce_max_over_ranks(x, world, torch.device("cpu"))
 
     from phylowgs_b200 import synth
     eng = P.Engine(device=local_rank, **synth.data_kwargs(s))
