@@ -1,0 +1,26 @@
+"""Times the grid kernel K2 (pwgs_llh_rows over all data) at config 3 for small and large trees."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import phylowgs_b200 as P
+from phylowgs_b200 import synth
+s = synth.config(3)
+eng = P.Engine(device=0, **synth.data_kwargs(s))
+rng = np.random.default_rng(1)
+D = s["a"].shape[0]
+for K in (11, 40, 120):
+    if K == 11:
+        parent, nod, phi, pi = s["parent"], s["node_of_datum"], s["phi"], s["pi"]
+    else:
+        parent = np.array([-1] + [int(rng.integers(0, k)) for k in range(1, K)], dtype=np.int32)
+        pi = rng.dirichlet(np.ones(K), size=1).T.copy(); phi = pi.copy()
+        for k in range(K - 1, 0, -1): phi[parent[k]] += phi[k]
+        nod = rng.integers(1, K, size=D).astype(np.int32)
+    t0 = time.perf_counter(); eng.set_tree(parent, nod, phi, pi); t1 = time.perf_counter()
+    rows = np.arange(D, dtype=np.int32)
+    eng.llh_rows(rows, 1)
+    ts = []
+    for _ in range(3):
+        t = time.perf_counter(); g = eng.llh_rows(rows, 1); ts.append(time.perf_counter() - t)
+    t = time.perf_counter(); tot = eng.total_llh(1); t2 = time.perf_counter() - t
+    print("K=%3d: set_tree %.2f ms, grid D x K = %d x %d: %.2f ms (%.1f MB out), total_llh %.2f ms" % (K, 1e3*(t1-t0), D, K, 1e3*min(ts), g.nbytes/1e6, 1e3*t2))

@@ -132,3 +132,17 @@ def test_mh_collapsed_plain_data_walks_the_same_chain(oracle, gpu_lib, ctas):
     assert got["ratio"] * iters == want["accepted"]
     assert rel(got["pi"], want["pi"]) < 1e-9
     assert rel(got["llh"], want["llh"]) < RTOL
+
+
+@pytest.mark.parametrize("K,T,iters,std", [(40, 1, 200, 2000.0), (35, 3, 120, 3000.0), (7, 2, 1, 1000.0), (2, 1, 150, 50.0)])
+def test_mh_trajectory_wide_trees_and_edge_sizes(oracle, gpu_lib, K, T, iters, std):
+    """More nodes than lanes in a warp (the proposal warp strides over nodes), several samples, a single iteration, a
+    two-node tree."""
+    data, tree = cases.synthetic_case(oracle, n_ssm=350, n_cnv=8, T=T, K=K, seed=30 + K)
+    want = oracle.mh_loop(data, tree, iters, std, oracle.RNG_PHILOX, 77, 5)
+    with cases.engine_for(gpu_lib, data, tree) as eng:
+        got = eng.mh_run(iters, std, 77, 5)
+    assert got["ratio"] * iters == pytest.approx(want["accepted"], abs=1e-9)
+    assert rel(got["pi"], want["pi"]) < 1e-9
+    assert rel(got["phi"], want["phi"]) < 1e-9
+    assert rel(got["llh"], want["llh"]) < RTOL
