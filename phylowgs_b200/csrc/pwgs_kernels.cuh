@@ -1,8 +1,10 @@
 // pwgs_kernels.cuh — the sm_100a kernels of libpwgs_b200.so.
-//   K0  lbc_kernel           log_bin_coeff(d,a) per datum x sample            (util.cpp:12-14 @ mh.cpp:234,284)
-//   K0b data_states_kernel   integer (nr,nv) state coefficients               (params.py:114-171)
-//   K1  mh_kernel<B>         persistent Metropolis-Hastings sampler           (mh.cpp:65-177, mh.hpp:80-163, util.cpp:24-33)
-//   K2  pair_llh_kernel      datum x candidate-node log-likelihoods           (data.py:26-126 / mh.hpp:80-163)
+//   K0  lbc_kernel            log_bin_coeff(d,a) per datum x sample            (util.cpp:12-14 @ mh.cpp:234,284)
+//   K0b data_states_kernel    dense integer (nr,nv) state coefficients         (params.py:114-171; diagnostics only)
+//   K0c cnv_sparse/sort/scatter  sparse, state-merged, sorted CNV work list    (what K1 reads instead of K0b's table)
+//   K0d collapse_kernel       integer totals of the plain data per (node, class, sample)   (opt-in "mh_collapse")
+//   K1  mh_kernel<STAGED>     persistent Metropolis-Hastings sampler           (mh.cpp:65-177, mh.hpp:80-163, util.cpp:24-33)
+//   K2  pair_llh_kernel       datum x candidate-node log-likelihoods           (data.py:26-126 / mh.hpp:80-163)
 // Citations are file:line relative to the reference checkout.
 #pragma once
 #include "pwgs_device.cuh"
