@@ -1,0 +1,87 @@
+"""-m gpu: the evolve / multievolve command lines end to end on the bundled example: output files and formats, status lines,
+checkpoint + resume after SIGTERM (exit code 3, evolve.py:434-472), chain merging."""
+import os
+import re
+import signal
+import subprocess
+import sys
+import time
+import zipfile
+
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SSM = os.path.join(cases.GOLDEN, "ssm_data.txt")
+CNV = os.path.join(cases.GOLDEN, "cnv_data.txt")
+ENV = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+
+
+def evolve(out, *extra, **kw):
+    cmd = [sys.executable, "-m", "phylowgs_b200.host.evolve", "-O", out] + list(extra) + [SSM, CNV]
+    return subprocess.run(cmd, env=ENV, cwd=ROOT, capture_output=True, text=True, timeout=600, **kw)
+
+
+def tree_names(out):
+    with zipfile.ZipFile(os.path.join(out, "trees.zip")) as z:
+        assert z.testzip() is None
+        return sorted(z.namelist())
+
+
+def test_evolve_cli_outputs(gpu_lib, tmp_path):
+    out = str(tmp_path / "run")
+    r = evolve(out, "-B", "6", "-s", "9", "-r", "4", "-i", "500")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    status = [l for l in r.stdout.splitlines() if "iteration=" in l]
+    assert len(status) == 15
+    last = dict(f.split("=", 1) for f in status[-1].split("] ", 1)[1].split(" "))
+    assert set(last) >= {"iteration", "trees_sampled", "total_trees", "llh", "nodes", "mh_acc", "dp_alpha", "dp_gamma", "alpha_decay"}
+    assert last["trees_sampled"] == "14" and last["total_trees"] == "15"
+    names = tree_names(out)
+    assert sum(n.startswith("tree_") for n in names) == 9 and sum(n.startswith("burnin_") for n in names) == 6
+    assert {"cnv_logical_physical_mapping.json", "params.json"} <= set(names)
+    assert open(os.path.join(out, "random_seed.txt")).read().strip() == "4"
+    rows = open(os.path.join(out, "mcmc_samples.txt")).read().strip().split("\n")
+    assert rows[0] == "Iteration\tLLH\tTime" and len(rows) == 16
+    for fn in ("state.initial.pickle", "state.last.pickle"):
+        assert os.path.exists(os.path.join(out, fn))
+    assert "Run succeeded." in r.stdout
+
+
+def test_evolve_resumes_after_sigterm_and_reproduces_the_uninterrupted_chain(gpu_lib, tmp_path):
+    args = ["-B", "10", "-s", "30", "-r", "8", "-i", "300", "-S", "5"]
+    ref = str(tmp_path / "straight")
+    assert evolve(ref, *args).returncode == 0
+    out = str(tmp_path / "interrupted")
+    cmd = [sys.executable, "-m", "phylowgs_b200.host.evolve", "-O", out] + args + [SSM, CNV]
+    p = subprocess.Popen(cmd, env=ENV, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    seen = 0
+    for line in p.stdout:                                   # let it write at least one checkpoint, then interrupt
+        if "iteration=" in line:
+            seen += 1
+            if seen == 13:
+                p.send_signal(signal.SIGTERM)
+                break
+    p.stdout.read()
+    assert p.wait(timeout=120) == 3                         # interrupted runs exit with 3 (evolve.py:464)
+    assert os.path.exists(os.path.join(out, "state.last.pickle"))
+    r = evolve(out)                                          # CLI ignored on resume except -O (evolve.py:347-349)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Resuming existing run" in r.stdout
+    assert tree_names(out) == tree_names(ref)                # member names carry index and LLH: the chain is the same chain
+
+
+def test_multievolve_two_chains_on_one_gpu(gpu_lib, tmp_path):
+    out = str(tmp_path / "chains")
+    cmd = [sys.executable, "-m", "phylowgs_b200.host.multievolve", "-n", "2", "-r", "1", "2", "-O", out, "--ssms", SSM, "--cnvs", CNV,
+           "-B", "4", "-s", "6", "-i", "300"]
+    r = subprocess.run(cmd, env=ENV, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    for i in range(2):
+        assert sum(n.startswith("tree_") for n in tree_names(os.path.join(out, "chain_%d" % i))) == 6
+    merged = tree_names(out)
+    n_trees = sum(n.startswith("tree_") for n in merged)
+    assert n_trees in (6, 12) and "params.json" in merged and not any(n.startswith("burnin") for n in merged)
+    assert re.search(r"Including chains", r.stdout)
