@@ -414,7 +414,7 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     const int stage = (c->opt_stage && smem + stage_bytes <= 224 * 1024) ? 1 : 0;
     if (stage) smem += stage_bytes;
     CUDA_TRY(c->partials.alloc((size_t)2 * PWGS_MAX_BATCH * cpc));
-    CUDA_TRY(c->ring.alloc((size_t)MH_RING * mh_bufstride(c->K, c->T, B)));
+    CUDA_TRY(c->ring.alloc((size_t)(MH_RING + 2) * mh_bufstride(c->K, c->T, B)));   // ring + the two epoch slots
     const int distributed = c->opt_dist < 0 ? (cpc >= MH_DIST_MIN_CTAS ? 1 : 0) : c->opt_dist;
     CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->abort_flag.p, 0, sizeof(int), c->stream));

@@ -389,7 +389,7 @@ struct MhSmem {
     __device__ __forceinline__ double *logr(int b) const { return buf0 + b * bufstride + o_logr; }
     double *red;                                    // [nb][warps per proposal group]: per-warp sums of the current batch
     double *llh;                                    // [MAXB]
-    double *pscratch;                               // [2K] producer warp: pi1 and phi1 of the proposal being drawn
+    double *pscratch;                               // [MH_CWARPS+1][2K] per warp: pi1 and phi1 of a proposal drawn for the ring
     volatile int *ctl;                              // producer mailbox, see MhCtl
     int *tin, *tout;                                // [K]
 };
@@ -400,7 +400,7 @@ __host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
 {
     size_t KT = (size_t)K * T;
     const size_t red = (size_t)maxb > MH_BU * MH_GWARPS ? (size_t)maxb : MH_BU * MH_GWARPS;
-    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 2 * K;
+    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 2 * (size_t)K * (MH_CWARPS + 1);
 }
 __host__ __device__ inline size_t mh_smem_ints(int K) { return CTL_WORDS + 2 * (size_t)K; }
 
@@ -746,10 +746,31 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
     }
 }
 
+// one warp draws (proposal b, sample tp) of a batch into a slot of the global ring, through its own shared-memory scratch
+__device__ __forceinline__ void mh_draw_to_slot(const MhParams &p, const MhSmem &S, int e, double *slot, int b, int tp, uint32_t it,
+                                                int scratch, int lane)
+{
+    const int T = p.T, K = p.K, KT = K * T;
+    double *x = S.pscratch + (size_t)scratch * 2 * K;
+    double hast = 0.0, logr = 0.0;
+    mh_propose(p, S, e, x, x + K, 1, &hast, &logr, tp, it, lane);
+    __syncwarp();
+#pragma unroll 1
+    for (int k = lane; k < K; k += 32) {
+        slot[(size_t)b * KT + k * T + tp] = x[k];
+        slot[(size_t)S.o_phi + (size_t)b * KT + k * T + tp] = x[K + k];
+    }
+    if (lane == 0) {
+        slot[(size_t)S.o_hast + b * T + tp] = hast;
+        if (tp == 0) slot[(size_t)S.o_logr + b] = logr;
+    }
+    __syncwarp();
+}
+
 // ---- the producer warp: draws the proposals this CTA owns of the batch two ahead and posts them in the global ring
 __device__ __noinline__ void mh_producer(const MhParams &p, const MhSmem &S, int rank, int cpc, int lane)
 {
-    const int T = p.T, K = p.K, KT = K * T;
+    const int T = p.T, K = p.K;
     const size_t slot_doubles = mh_bufstride(K, T, p.max_batch);
     int job = 1;                                                                // jobs are numbered by global batch, from 1
 #pragma unroll 1
@@ -764,25 +785,53 @@ __device__ __noinline__ void mh_producer(const MhParams &p, const MhSmem &S, int
         for (int task = 0; task < nb * T; task++) {
             if ((task + job * 37) % cpc != rank) continue;                       // one owner CTA per (proposal, sample)
             const int b = task / T, tp = task - b * T;
-            double hast = 0.0, logr = 0.0;
-            mh_propose(p, S, e, S.pscratch, S.pscratch + K, 1, &hast, &logr, tp, (uint32_t)(it_first + b), lane);
-            __syncwarp();
-#pragma unroll 1
-            for (int k = lane; k < K; k += 32) {
-                slot[(size_t)b * KT + k * T + tp] = S.pscratch[k];
-                slot[(size_t)S.o_phi + (size_t)b * KT + k * T + tp] = S.pscratch[K + k];
-            }
-            if (lane == 0) {
-                slot[(size_t)S.o_hast + b * T + tp] = hast;
-                if (tp == 0) slot[(size_t)S.o_logr + b] = logr;
-            }
-            __syncwarp();
+            mh_draw_to_slot(p, S, e, slot, b, tp, (uint32_t)(it_first + b), MH_CWARPS, lane);
         }
         __threadfence();                                                         // ring stores ordered before the "done" flag
         __syncwarp();
         if (lane == 0) S.ctl[CTL_PROD_DONE] = job;
         job++;
     }
+}
+
+// Start of an epoch (right after an accept) in distributed mode: the first two batches of the new epoch are drawn once per
+// chain as well.  Every (proposal, sample) has one owner warp somewhere in the chain, the draws land in the two epoch slots
+// of the ring, and one extra chain barrier makes them visible; the first batch is then fetched into proposal buffer `buf`.
+// (Drawing them redundantly in every CTA cost ~10k cycles per 11 proposals and dominated the price of an accept.)
+// Out of line on purpose: it is cold code and must not disturb the register allocation of the likelihood loops.
+// Returns true if the watchdog fired.
+__device__ __noinline__ bool mh_epoch_start(const MhParams &p, const MhSmem &S, int e, int buf, int n0, int it0, int n1, int rank, int cpc,
+                                            unsigned long long bar_no, int tid, int warp, int lane)
+{
+    const int T = p.T, KT = p.K * T, it1 = it0 + n0, total = (n0 + n1) * T;
+    double *es0 = p.ring + (size_t)MH_RING * (size_t)S.bufstride, *es1 = es0 + S.bufstride;
+#pragma unroll 1
+    for (int li = warp; li * cpc + rank < total; li += MH_CWARPS) {
+        const int t = li * cpc + rank, bsel = t / T, tp = t - bsel * T;
+        if (bsel < n0) mh_draw_to_slot(p, S, e, es0, bsel, tp, (uint32_t)(it0 + bsel), warp, lane);
+        else mh_draw_to_slot(p, S, e, es1, bsel - n0, tp, (uint32_t)(it1 + bsel - n0), warp, lane);
+    }
+    __threadfence();
+    consumer_sync();
+    if (tid == 0) {
+        red_release_add(p.counter, 1ull);
+        const unsigned long long target = (bar_no + 1) * (unsigned long long)cpc;
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        while (ld_acquire(p.counter) < target)
+            if ((++spins & 0xff) == 0 && (*(volatile int *)p.abort_flag || clock64() - t0 > MH_WATCHDOG_CYCLES)) {
+                atomicExch(p.abort_flag, 1);
+                S.ctl[CTL_ABORT] = 1;
+                break;
+            }
+    }
+    consumer_sync();
+    if (S.ctl[CTL_ABORT]) return true;
+    double *dst = S.prop_pi(buf);
+    for (int i = tid; i < n0 * KT; i += MH_CONSUMERS) { dst[i] = __ldcg(es0 + i); dst[S.o_phi + i] = __ldcg(es0 + S.o_phi + i); }
+    for (int i = tid; i < n0 * T; i += MH_CONSUMERS) dst[S.o_hast + i] = __ldcg(es0 + S.o_hast + i);
+    for (int i = tid; i < n0; i += MH_CONSUMERS) dst[S.o_logr + i] = __ldcg(es0 + S.o_logr + i);
+    return false;
 }
 
 // One chain = cpc co-resident CTAs (cooperative launch).  Every CTA keeps the node table in shared memory, evaluates its slice
@@ -815,7 +864,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = MAXB * KT; S.o_hast = 2 * MAXB * KT; S.o_logr = 2 * MAXB * KT + MAXB * T;
         S.buf0 = q; q += 2 * S.bufstride;
         S.red = q; q += (MAXB > MH_BU * MH_GWARPS ? MAXB : MH_BU * MH_GWARPS); S.llh = q; q += MAXB;
-        S.pscratch = q; q += 2 * K;
+        S.pscratch = q; q += 2 * K * (MH_CWARPS + 1);
         S.ctl = (volatile int *)q; S.tin = (int *)q + CTL_WORDS; S.tout = S.tin + K;
     }
     for (int i = tid; i < KT; i += MH_THREADS) {
@@ -893,7 +942,9 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
     int b_it = 0, b_nb = 1;                            // current batch: first iteration, size
     int j = -1;                                        // batches since the last accept; -1: the initial evaluation of the entry state
     int accepted = 0;
-    int g = 0;                                         // global batch number == barrier number
+    int g = 0;                                         // global batch number (proposal ring slots, partial-sum parity)
+    unsigned long long bar_no = 0;                     // chain barriers passed so far (one per batch + one per accept)
+    bool es_ready = false;                             // the second batch of the current epoch waits in epoch slot 1
     double cur_llh = 0.0;
 
 #pragma unroll 1
@@ -952,11 +1003,11 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         MH_PROF(1);
 
         // ---------------- while the barrier is in flight: draw the next batch locally when the ring cannot provide it
-        const bool next_local = !dist || j <= 0;
+        const bool next_local = !dist || j < 0 || (j == 0 && !es_ready);
         if (next_local) mh_draw_local(p, S, e, cur ^ 1, n1_nb, n1_it, warp, lane);
         MH_PROF(2);
         if (tid == 0) {
-            const unsigned long long target = (unsigned long long)(g + 1) * (unsigned long long)cpc;
+            const unsigned long long target = (bar_no + 1) * (unsigned long long)cpc;
             const long long t0 = clock64();
             unsigned spins = 0;
             while (ld_acquire(p.counter) < target)
@@ -966,6 +1017,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
                     break;
                 }
         }
+        bar_no++;
         consumer_sync();
         if (S.ctl[CTL_ABORT]) break;
         MH_PROF(3);
@@ -974,7 +1026,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         // the loads of the next batch's ring slot (complete: every CTA posted its share before arriving) go out first so that
         // all L2 round trips of this step overlap
         const bool fetch = !next_local && n1_nb > 0;
-        const double *slot = p.ring + (size_t)((g + 1) % MH_RING) * (size_t)S.bufstride;
+        const double *slot = p.ring + (size_t)(j == 0 ? MH_RING + 1 : (g + 1) % MH_RING) * (size_t)S.bufstride;   // epoch slot 1 / ring
         double f_pi = 0.0, f_phi = 0.0, f_h = 0.0, f_r = 0.0;
         if (fetch) {
             if (tid < n1_nb * KT) { f_pi = __ldcg(slot + tid); f_phi = __ldcg(slot + S.o_phi + tid); }
@@ -1055,7 +1107,15 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         consumer_sync();
         mh_refresh_state(p, S, e, tid, warp, lane);
         consumer_sync();
-        mh_draw_local(p, S, e, cur ^ 1, b_nb, b_it, warp, lane);
+        es_ready = false;
+        if (!dist) {
+            mh_draw_local(p, S, e, cur ^ 1, b_nb, b_it, warp, lane);
+        } else {
+            const int n1b = next_batch(b_nb, p.iters - (b_it + b_nb), MAXB);
+            if (mh_epoch_start(p, S, e, cur ^ 1, b_nb, b_it, n1b, rank, cpc, bar_no, tid, warp, lane)) break;
+            bar_no++;
+            es_ready = n1b > 0;
+        }
         cur ^= 1;
         consumer_sync();
         MH_PROF(6);
