@@ -175,7 +175,7 @@ class TreeWriter(object):
             rm_safely(self.default_archive_fn)
 
     def _open(self):
-        return zipfile.ZipFile(self.default_archive_fn, "a", compression=zipfile.ZIP_DEFLATED, allowZip64=True)
+        return zipfile.ZipFile(self.default_archive_fn, "a", compression=zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=1)
 
     def add_extra_file(self, filename, data):
         with self._open() as z:
