@@ -1035,9 +1035,10 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         }
         {
             const double *pp = p.partials + (size_t)parity * PWGS_MAX_BATCH * cpc;
+            const int rot = (rank * 13) & (b_nb - 1);                           // CTAs walk the proposals in rotated order so that the
 #pragma unroll 1
-            for (int bq = warp; bq < b_nb; bq += 2 * MH_CWARPS) {                // two proposals per warp and pass
-                const int b0 = bq, b1 = bq + MH_CWARPS;
+            for (int bq = warp; bq < b_nb; bq += 2 * MH_CWARPS) {                // chain does not hammer the same L2 lines at once
+                const int b0 = (bq + rot) & (b_nb - 1), b1 = bq + MH_CWARPS < b_nb ? ((bq + MH_CWARPS + rot) & (b_nb - 1)) : b_nb;
                 double v0[5], v1[5];
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
