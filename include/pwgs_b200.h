@@ -161,6 +161,10 @@ typedef struct pwgs_sweep {
 } pwgs_sweep;
 int pwgs_resample_assignments(pwgs_sweep *sweep);
 
+/* Diagnostics: the MH kernel's branch-free fp64 routines on caller-supplied arguments x[n] (positive, normal):
+ * out[0..n) = log(x), out[n..2n) = exp(-x), out[2n..3n) = x / (1 + x).  Used by the accuracy test. */
+int pwgs_math_selftest(int device, int n, const double *x, double *out);
+
 /* Measured FP64-pipe issue peak of the device (DFMA chains, thread-instructions/s) — the roofline
  * denominator for the MH kernel, which is FP64-pipe-bound, not HBM-bound. */
 int pwgs_fp64_peak(int device, double *dfma_per_s);

@@ -671,6 +671,21 @@ int pwgs_get_stream(pwgs_ctx *c, void **stream)
     return PWGS_OK;
 }
 
+int pwgs_math_selftest(int device, int n, const double *x, double *out)
+{
+    if (!x || !out || n <= 0) return fail(PWGS_EINVAL, "bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    double *dx = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&dx, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc((void **)&dout, sizeof(double) * 3 * (size_t)n));
+    CUDA_TRY(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    math_selftest_kernel<<<(n + 4 * 128 - 1) / (4 * 128), 128>>>(n, dx, dout);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, dout, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dout);
+    return PWGS_OK;
+}
+
 int pwgs_fp64_peak(int device, double *dfma_per_s)
 {
     if (!dfma_per_s) return fail(PWGS_EINVAL, "NULL argument");

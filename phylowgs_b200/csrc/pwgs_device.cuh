@@ -162,10 +162,8 @@ __device__ __forceinline__ void pwgs_log_pos_n(const double (&x)[N], double (&r)
     for (int i = 0; i < N; i++) d[i] = 2.0 + f[i];
 #pragma unroll
     for (int i = 0; i < N; i++) y[i] = pwgs_rcp_approx(d[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(-d[i], y[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);
+    // y ~ 1/d to 2^-20 from the hardware; one Newton step (2^-40) is enough because the residual correction of the quotient
+    // below squares the error once more (q = q0 + (f - d*q0)*y: relative error 2^-80 before rounding)
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] = fma(-d[i], y[i], 1.0);
 #pragma unroll
@@ -216,11 +214,7 @@ __device__ __forceinline__ void pwgs_div_pos_n(const double (&a)[N], const doubl
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] = fma(-b[i], y[i], 1.0);
 #pragma unroll
-    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(-b[i], y[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);
+    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);                  // 2^-40; the correction below gives 2^-80
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = a[i] * y[i];
 #pragma unroll

@@ -1131,6 +1131,24 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
     }
 }
 
+// ============================================================================ math self-test (diagnostics)
+// out[0][i] = pwgs_log_pos_n(x[i]) (the MH kernel's logarithm), out[1][i] = pwgs_exp_nonpos_n(-x[i]), out[2][i] = x[i] / (1 + x[i])
+// through pwgs_div_pos_n; four values per thread, like the kernel uses them.
+__global__ void math_selftest_kernel(int n, const double *__restrict__ x, double *__restrict__ out)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    double v[4], l[4], e[4], nx[4], den[4], q[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = x[min(i + k, n - 1)]; nx[k] = -v[k]; den[k] = 1.0 + v[k]; }
+    pwgs_log_pos_n<4>(v, l);
+    pwgs_exp_nonpos_n<4>(nx, e);
+    pwgs_div_pos_n<4>(v, den, q);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (i + k < n) { out[i + k] = l[k]; out[n + i + k] = e[k]; out[2 * (size_t)n + i + k] = q[k]; }
+}
+
 // ============================================================================ FP64 peak probe
 __global__ void dfma_peak_kernel(int iters, double seed, double *out)
 {

@@ -146,3 +146,25 @@ def test_mh_trajectory_wide_trees_and_edge_sizes(oracle, gpu_lib, K, T, iters, s
     assert rel(got["pi"], want["pi"]) < 1e-9
     assert rel(got["phi"], want["phi"]) < 1e-9
     assert rel(got["llh"], want["llh"]) < RTOL
+
+
+def test_device_log_exp_div_accuracy(gpu_lib):
+    """The MH kernel's own branch-free fp64 log / exp / division (csrc/pwgs_device.cuh) against numpy: a few ulp at most."""
+    import ctypes as C
+    from phylowgs_b200 import _lib
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(1e-6, 1.0, 20000), rng.uniform(1.0, 700.0, 20000), 10.0 ** rng.uniform(-300, 300, 20000),
+                        np.array([1.0, 0.5, 2.0, 0.999, 0.001, 0.499, 0.7071067811865476, 1.4142135623730951, np.nextafter(1.0, 0), np.nextafter(1.0, 2)])])
+    out = np.zeros(3 * len(x))
+    _lib.check(_lib.load().pwgs_math_selftest(0, len(x), _lib.p_f64(x), _lib.p_f64(out)))
+    lg, ex, dv = out[:len(x)], out[len(x):2 * len(x)], out[2 * len(x):]
+    want = np.log(x)
+    err = np.abs(lg - want) / np.maximum(np.spacing(np.abs(want)), 1e-300)
+    assert err.max() <= 2.0, (err.max(), x[err.argmax()])
+    small = x <= 700.0
+    want_e = np.exp(-x[small])
+    err_e = np.abs(ex[small] - want_e) / np.spacing(want_e)
+    assert err_e.max() <= 4.0, (err_e.max(), x[small][err_e.argmax()])
+    big = x < 1e150
+    want_d = x[big] / (1.0 + x[big])
+    assert (np.abs(dv[big] - want_d) / np.spacing(want_d)).max() <= 1.0
