@@ -446,7 +446,15 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
 
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     const void *kfn = stage ? (const void *)mh_kernel<true> : (const void *)mh_kernel<false>;
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the attribute belongs to the function, not to the launch: chains running as threads of one process launch with
+    // different sizes concurrently, so it is always set to the one value every launch fits under
+    int smem_optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    cudaFuncAttributes kattr;
+    CUDA_TRY(cudaFuncGetAttributes(&kattr, kfn));
+    const int smem_dyn_max = smem_optin - (int)kattr.sharedSizeBytes;      // the limit covers static + dynamic
+    if (smem > (size_t)smem_dyn_max) return fail(PWGS_ELIMIT, "shared-memory node table exceeds the device's per-block limit");
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dyn_max);
     if (e == cudaSuccess) {
         const MhParams *plist = c->plist.p;
         void *args[] = {(void *)&plist, (void *)&cpc};

@@ -141,22 +141,28 @@ class StateManager(object):
     default_last_state_fn = "state.last.pickle"
     default_initial_state_fn = "state.initial.pickle"
 
+    def __init__(self, workdir="."):
+        # every chain file is addressed through its directory, never through the process' cwd: several chains can then
+        # share one process (multievolve --in-process)
+        self.last_state_fn = os.path.join(workdir, self.default_last_state_fn)
+        self.initial_state_fn = os.path.join(workdir, self.default_initial_state_fn)
+
     def _dump(self, state, fn):
         with open(fn, "wb") as f:
             pickle.dump(state, f, protocol=2)
 
     def write_state(self, state):
-        self._dump(state, self.default_last_state_fn)
+        self._dump(state, self.last_state_fn)
 
     def write_initial_state(self, state):
-        self._dump(state, self.default_initial_state_fn)
+        self._dump(state, self.initial_state_fn)
 
     def load_state(self):
-        with open(self.default_last_state_fn, "rb") as f:
+        with open(self.last_state_fn, "rb") as f:
             return pickle.load(f)
 
     def state_exists(self):
-        return os.path.isfile(self.default_last_state_fn)
+        return os.path.isfile(self.last_state_fn)
 
 
 class CorruptZipFileError(Exception):
@@ -166,16 +172,17 @@ class CorruptZipFileError(Exception):
 class TreeWriter(object):
     default_archive_fn = "trees.zip"
 
-    def __init__(self, resume_run=False):
+    def __init__(self, resume_run=False, workdir="."):
+        self.archive_fn = os.path.join(workdir, self.default_archive_fn)
         if resume_run:
-            with zipfile.ZipFile(self.default_archive_fn) as z:
+            with zipfile.ZipFile(self.archive_fn) as z:
                 if z.testzip() is not None:
-                    raise CorruptZipFileError("Corrupt zip file: %s" % self.default_archive_fn)
+                    raise CorruptZipFileError("Corrupt zip file: %s" % self.archive_fn)
         else:
-            rm_safely(self.default_archive_fn)
+            rm_safely(self.archive_fn)
 
     def _open(self):
-        return zipfile.ZipFile(self.default_archive_fn, "a", compression=zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=1)
+        return zipfile.ZipFile(self.archive_fn, "a", compression=zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=1)
 
     def add_extra_file(self, filename, data):
         with self._open() as z:
@@ -188,11 +195,21 @@ class TreeWriter(object):
 
 
 # ------------------------------------------------------------------ the chain
-def _attach(state, codes):
+def chain_device_index(config):
+    """The chain's GPU: config["device"] (multievolve --in-process) or PWGS_DEVICE (one process per chain), default 0."""
+    dev = config.get("device")
+    return int(os.environ.get("PWGS_DEVICE", "0")) if dev is None else int(dev)
+
+
+def chain_log(config, msg, fd=None):
+    logmsg(config.get("log_prefix", "") + msg, fd)
+
+
+def _attach(state, codes, config):
     """(Re)create the process-local parts of a chain: its generator and its device context."""
     tssb = state["tssb"]
     tssb.rng = np.random.RandomState()
-    tssb.backend = GpuBackend(codes, device=int(os.environ.get("PWGS_DEVICE", "0")))
+    tssb.backend = GpuBackend(codes, device=chain_device_index(config))
     tssb.data = codes
     for d in codes:
         d.tssb = tssb
@@ -200,24 +217,26 @@ def _attach(state, codes):
 
 
 def start_new_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config, ssm_file, cnv_file, params_file,
-                  burnin_samples, num_samples, mh_itr, mh_std, write_state_every, write_backups_every, rand_seed, tmp_dir):
+                  burnin_samples, num_samples, mh_itr, mh_std, write_state_every, write_backups_every, rand_seed, tmp_dir,
+                  workdir="."):
     state = {}
+    seed_fn = os.path.join(workdir, "random_seed.txt")
     if rand_seed is not None:
         state["rand_seed"] = int(rand_seed)
     else:                                       # CLI -> random_seed.txt -> fresh seed (evolve.py:33-53)
         try:
-            with open("random_seed.txt") as f:
+            with open(seed_fn) as f:
                 state["rand_seed"] = int(f.read().strip())
         except (OSError, ValueError):
             state["rand_seed"] = int(np.random.randint(2 ** 32, dtype=np.uint64))
-    with open("random_seed.txt", "w") as f:
+    with open(seed_fn, "w") as f:
         f.write("%s\n" % state["rand_seed"])
-    state.update(working_dir=os.getcwd(), ssm_file=ssm_file, cnv_file=cnv_file, tmp_dir=tmp_dir,
+    state.update(working_dir=os.path.abspath(workdir), ssm_file=ssm_file, cnv_file=cnv_file, tmp_dir=tmp_dir,
                  write_state_every=write_state_every, write_backups_every=write_backups_every)
 
     codes, n_ssms, n_cnvs, mapping = load_data(ssm_file, cnv_file)
     if not codes:
-        logmsg("No SSMs or CNVs provided. Exiting.", sys.stderr)
+        chain_log(config, "No SSMs or CNVs provided. Exiting.", sys.stderr)
         return
     ntps = len(codes[0].a)
     state["glist"] = [d.name for d in codes if len(d.name) > 0]
@@ -227,7 +246,7 @@ def start_new_run(state_manager, backup_manager, safe_to_exit, run_succeeded, co
     state["burnin_cd_llh_traces"] = np.zeros((burnin_samples, 1))
 
     rng = np.random.RandomState(state["rand_seed"])
-    backend = GpuBackend(codes, device=int(os.environ.get("PWGS_DEVICE", "0")))
+    backend = GpuBackend(codes, device=chain_device_index(config))
     root = alleles(conc=0.1, ntps=ntps)
     tssb = TSSB(dp_alpha=state["dp_alpha"], dp_gamma=state["dp_gamma"], alpha_decay=state["alpha_decay"], root_node=root,
                 data=codes, rng=rng, backend=backend)
@@ -244,7 +263,7 @@ def start_new_run(state_manager, backup_manager, safe_to_exit, run_succeeded, co
         d.tssb = tssb
     state["tssb"] = tssb
 
-    writer = TreeWriter()
+    writer = TreeWriter(workdir=workdir)
     writer.add_extra_file("cnv_logical_physical_mapping.json", json.dumps(mapping))
     params = {}
     if params_file is not None:
@@ -253,37 +272,41 @@ def start_new_run(state_manager, backup_manager, safe_to_exit, run_succeeded, co
     writer.add_extra_file("params.json", json.dumps(params))
 
     state_manager.write_initial_state(state)
-    logmsg("Starting MCMC run...")
+    chain_log(config, "Starting MCMC run...")
     state["last_iteration"] = -state["burnin"] - 1
-    with open("mcmc_samples.txt", "w") as f:
+    with open(os.path.join(workdir, "mcmc_samples.txt"), "w") as f:
         f.write("Iteration\tLLH\tTime\n")
-    do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, state, writer, codes, n_ssms, n_cnvs, ntps, tmp_dir)
+    do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, state, writer, codes, n_ssms, n_cnvs, ntps, tmp_dir,
+            workdir)
 
 
-def resume_existing_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config):
+def resume_existing_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config, workdir="."):
+    # the reference chdir()s into state["working_dir"] here (evolve.py:262); that is the directory the state was just read
+    # from, and the one every path below is built on
     try:
         state = state_manager.load_state()
-        os.chdir(state["working_dir"])
-        writer = TreeWriter(resume_run=True)
+        writer = TreeWriter(resume_run=True, workdir=workdir)
     except Exception:
-        logmsg("Restoring state failed:", sys.stderr)
+        chain_log(config, "Restoring state failed:", sys.stderr)
         traceback.print_exc()
-        logmsg("Restoring from backup and trying again.", sys.stderr)
+        chain_log(config, "Restoring from backup and trying again.", sys.stderr)
         backup_manager.restore_backup()
         state = state_manager.load_state()
-        os.chdir(state["working_dir"])
-        writer = TreeWriter(resume_run=True)
+        writer = TreeWriter(resume_run=True, workdir=workdir)
+    state["working_dir"] = os.path.abspath(workdir)
     tssb = state["tssb"]
     codes = tssb.data                           # the pickled data carry the assignments' bookkeeping (datum.node)
     n_ssms = sum(1 for d in codes if d.id[0] == "s")
-    _attach(state, codes)
+    _attach(state, codes, config)
     tssb.rng.set_state(state["rand_state"])
     do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, state, writer, codes, n_ssms, len(codes) - n_ssms,
-            len(codes[0].a), state["tmp_dir"])
+            len(codes[0].a), state["tmp_dir"], workdir)
 
 
 def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, state, tree_writer, codes, n_ssms, n_cnvs, ntps,
-            tmp_dir_parent):
+            tmp_dir_parent, workdir="."):
+    samples_fn = os.path.join(workdir, "mcmc_samples.txt")
+    on_status = config.get("on_status")           # multievolve --in-process reads the progress here instead of from a pipe
     start_iter = state["last_iteration"] + 1
     unwritten, sample_times = [], []
     t_last = time.time()
@@ -311,10 +334,10 @@ def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, 
         acc = float(state["mh_acc"])
         if acc < 0.08 and state["mh_std"] < 10000:
             state["mh_std"] = state["mh_std"] * 2.0
-            logmsg("Shrinking MH proposals. Now %f" % state["mh_std"])
+            chain_log(config, "Shrinking MH proposals. Now %f" % state["mh_std"])
         if 0.5 < acc < 0.99:
             state["mh_std"] = state["mh_std"] / 2.0
-            logmsg("Growing MH proposals. Now %f" % state["mh_std"])
+            chain_log(config, "Growing MH proposals. Now %f" % state["mh_std"])
 
         tssb.resample_sticks()
         tssb.resample_stick_orders()
@@ -331,13 +354,16 @@ def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, 
             status["alpha_decay"] = tssb.alpha_decay
         else:
             state["burnin_cd_llh_traces"][iteration + state["burnin"]] = last_llh
-        logmsg(" ".join("%s=%s" % kv for kv in status.items()))
+        if on_status is not None:
+            on_status(status)
+        else:
+            logmsg(" ".join("%s=%s" % kv for kv in status.items()))
 
         unwritten.append((pickle.dumps(tssb, protocol=2), iteration, last_llh))
         state["rand_state"] = tssb.rng.get_state()
         state["last_iteration"] = iteration
         if len([c for c in tssb.root["children"] if c["node"].has_data()]) > 1:
-            logmsg("Polyclonal tree detected with %s clones." % len(tssb.root["children"]))
+            chain_log(config, "Polyclonal tree detected with %s clones." % len(tssb.root["children"]))
 
         now = time.time()
         sample_times.append(now - t_last)
@@ -347,7 +373,7 @@ def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, 
         write_backup = iteration % state["write_backups_every"] == 0 and iteration != start_iter
         write_state = iteration % state["write_state_every"] == 0
         if write_backup or write_state or iteration == state["num_samples"] - 1:
-            with open("mcmc_samples.txt", "a") as f:
+            with open(samples_fn, "a") as f:
                 f.write("\n".join("%s\t%s\t%s" % (it, llh, dt) for (_, it, llh), dt in zip(unwritten, sample_times)) + "\n")
             tree_writer.write_trees(unwritten)
             state_manager.write_state(state)
@@ -386,14 +412,15 @@ def run(safe_to_exit, run_succeeded, config, argv=None):
     install_pickle_aliases()
     known, _ = create_argparser(full=False).parse_known_args(argv)
     orig_dir = os.getcwd()
+    workdir = orig_dir                            # the reference chdir()s here (evolve.py:341-344); we carry the path instead
     if known.output_dir is not None:
-        os.makedirs(known.output_dir, exist_ok=True)
-        os.chdir(known.output_dir)
-    state_manager = StateManager()
-    backup_manager = BackupManager([StateManager.default_last_state_fn, TreeWriter.default_archive_fn])
+        workdir = os.path.abspath(known.output_dir)
+        os.makedirs(workdir, exist_ok=True)
+    state_manager = StateManager(workdir)
+    backup_manager = BackupManager([state_manager.last_state_fn, os.path.join(workdir, TreeWriter.default_archive_fn)])
     if state_manager.state_exists():
-        logmsg("Resuming existing run. Ignoring command-line parameters (except --output-dir).")
-        resume_existing_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config)
+        chain_log(config, "Resuming existing run. Ignoring command-line parameters (except --output-dir).")
+        resume_existing_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config, workdir)
         return
     args = create_argparser().parse_args(argv)
     paths = {}
@@ -409,7 +436,8 @@ def run(safe_to_exit, run_succeeded, config, argv=None):
     start_new_run(state_manager, backup_manager, safe_to_exit, run_succeeded, config, paths["ssm_file"], paths["cnv_file"],
                   paths["params_file"], burnin_samples=args.burnin_samples, num_samples=args.mcmc_samples,
                   mh_itr=args.mh_iterations, mh_std=100, write_state_every=args.write_state_every,
-                  write_backups_every=args.write_backups_every, rand_seed=args.random_seed, tmp_dir=paths["tmp_dir"])
+                  write_backups_every=args.write_backups_every, rand_seed=args.random_seed, tmp_dir=paths["tmp_dir"],
+                  workdir=workdir)
 
 
 def remove_tmp_files(tmp_dir):

@@ -3,7 +3,9 @@
     python -m phylowgs_b200.host.multievolve -n 8 [-r s0 s1 ...] [-I 1.1] [-O chains] --ssms ssm.txt --cnvs cnv.txt [evolve options]
 
 Chains share nothing (multievolve.py:85-90), so chain i runs as its own `evolve` process pinned to GPU i mod n_gpus through
-PWGS_DEVICE — no collective, no NCCL.  Afterwards the chains whose log-sum of tree likelihoods is within the inclusion factor
+PWGS_DEVICE — no collective, no NCCL.  With --in-process the chains are threads of this process instead (one device context
+and stream per chain; ctypes releases the GIL during every library call, so one chain's host work overlaps the others' kernels
+and native sweeps): several chains per GPU then share one CUDA context instead of time-slicing between processes.  Afterwards the chains whose log-sum of tree likelihoods is within the inclusion factor
 of the best one are merged into <output-dir>/trees.zip with re-indexed tree members (multievolve.py:215-313).
 """
 import argparse
@@ -37,6 +39,8 @@ def parse_args(argv=None):
     p.add_argument("--cnvs", dest="cnv_file", required=True, help="File listing CNVs")
     p.add_argument("--gpus", dest="gpus", default=None,
                    help="Comma-separated device indices to spread the chains over (default: all visible devices)")
+    p.add_argument("--in-process", dest="in_process", action="store_true",
+                   help="Run the chains as threads of this process (one CUDA context per GPU) instead of one process per chain")
     known, other = p.parse_known_args(argv)
     return vars(known), other
 
@@ -114,6 +118,71 @@ def watch_chains(processes, poll=1.0):
     return [status[i].get("exit_code") for i in range(n)]
 
 
+def run_chains_in_process(chain_dirs, ssm_fn, cnv_fn, seeds, other_args, devices, poll=1.0):
+    """All chains as threads of this process, each driving evolve.run with its own directory, device and status callback.
+    -> exit codes like watch_chains (0 succeeded, 1 failed).  SIGTERM / SIGINT wait until every chain is between file writes,
+    then exit 3 (each chain resumes from its state.last.pickle on the next run)."""
+    import signal
+    from . import evolve
+    n = len(chain_dirs)
+    status = {i: {"status": "initializing"} for i in range(n)}
+    chains = []
+    # a chain coming back from a library call must get the GIL back from whichever chain is running Python; the default
+    # 5 ms hand-over interval would add up to more than the calls themselves
+    sys.setswitchinterval(float(os.environ.get("PWGS_SWITCH_INTERVAL", "2e-4")))
+    for i, d in enumerate(chain_dirs):
+        argv = ["--output-dir", d]
+        if seeds is not None:
+            argv += ["--random-seed", str(seeds[i])]
+        argv += [ssm_fn, cnv_fn] + list(other_args)
+
+        def on_status(st, i=i):
+            st = dict(st, status="running")
+            st["percent_complete"] = "{:.2f}%".format(100 * float(st["trees_sampled"]) / float(st["total_trees"]))
+            status[i] = st
+        safe, ok = threading.Event(), threading.Event()
+        safe.set()
+        config = {"tmp_dir": None, "device": chain_device(i, devices), "log_prefix": "chain=%d " % i, "on_status": on_status}
+
+        def body(safe=safe, ok=ok, config=config, argv=argv):
+            try:
+                evolve.run(safe, ok, config, argv)
+            except SystemExit:
+                pass
+            except Exception:
+                import traceback
+                logmsg(config["log_prefix"] + "failed:", sys.stderr)
+                traceback.print_exc()
+        logmsg("Starting chain %s on GPU %s (in-process)" % (i, config["device"]))
+        th = threading.Thread(target=body, daemon=True)
+        chains.append((th, safe, ok, config))
+
+    def on_signal(signo, _frame):
+        logmsg("Signal %s received." % signo, sys.stderr)
+        for _, safe, _, config in chains:
+            safe.wait()
+        for _, _, _, config in chains:
+            evolve.remove_tmp_files(config["tmp_dir"])
+        logmsg("Exiting now.")
+        os._exit(3)             # the chain threads are mid-iteration by design; nothing is being written (all safe events held)
+    if threading.current_thread() is threading.main_thread():
+        signal.signal(signal.SIGTERM, on_signal)
+        signal.signal(signal.SIGINT, on_signal)
+    for th, _, _, _ in chains:
+        th.start()
+    while any(th.is_alive() for th, _, _, _ in chains):
+        time.sleep(poll)
+        for i, (th, _, ok, _) in enumerate(chains):
+            if not th.is_alive():
+                status[i] = {"status": "done", "exit_code": 0 if ok.is_set() else 1}
+            st = status[i]
+            keys = {"running": ("trees_sampled", "total_trees", "percent_complete"), "done": ("exit_code",)}.get(st["status"], ())
+            logmsg("chain={} {}".format(i, " ".join("{}={}".format(k, st[k]) for k in ("status",) + keys)))
+    for _, _, _, config in chains:
+        evolve.remove_tmp_files(config["tmp_dir"])
+    return [0 if ok.is_set() else 1 for _, _, ok, _ in chains]
+
+
 def logsumexp(x):
     x = np.asarray(x, dtype=float)
     m = np.max(x)
@@ -170,13 +239,18 @@ def main(argv=None):
                          % (args["num_chains"], len(args["random_seeds"])))
     devices = visible_devices(args["gpus"])
     ssm, cnv = os.path.abspath(args["ssm_file"]), os.path.abspath(args["cnv_file"])
-    procs, dirs = [], []
-    for i in range(args["num_chains"]):
-        d = os.path.join(args["output_dir"], "chain_%d" % i)
+    dirs = [os.path.join(args["output_dir"], "chain_%d" % i) for i in range(args["num_chains"])]
+    for d in dirs:
         os.makedirs(d, exist_ok=True)
-        dirs.append(d)
-        procs.append(run_chain(i, ssm, cnv, os.getcwd(), d, args["random_seeds"], evolve_args, chain_device(i, devices)))
-    watch_chains(procs)
+    if args["in_process"]:
+        codes = run_chains_in_process(dirs, ssm, cnv, args["random_seeds"], evolve_args, devices)
+    else:
+        procs = [run_chain(i, ssm, cnv, os.getcwd(), d, args["random_seeds"], evolve_args, chain_device(i, devices))
+                 for i, d in enumerate(dirs)]
+        codes = watch_chains(procs)
+    if any(codes):
+        logmsg("Chains %s failed; not merging." % [i for i, c in enumerate(codes) if c], sys.stderr)
+        sys.exit(1)
     inc, exc = determine_chains_to_merge(dirs, args["chain_inclusion_factor"])
     merge_best_chains(args["output_dir"], dirs, inc, exc)
 

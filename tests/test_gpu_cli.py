@@ -85,3 +85,25 @@ def test_multievolve_two_chains_on_one_gpu(gpu_lib, tmp_path):
     n_trees = sum(n.startswith("tree_") for n in merged)
     assert n_trees in (6, 12) and "params.json" in merged and not any(n.startswith("burnin") for n in merged)
     assert re.search(r"Including chains", r.stdout)
+
+
+def test_multievolve_in_process_chains_equal_the_per_process_chains(gpu_lib, tmp_path):
+    """--in-process runs the chains as threads of one process (one CUDA context): same seeds -> the same chains, file for
+    file, as one evolve process per chain."""
+    base = [sys.executable, "-m", "phylowgs_b200.host.multievolve", "-n", "3", "-r", "5", "6", "7", "--ssms", SSM, "--cnvs", CNV,
+            "-B", "5", "-s", "8", "-i", "300"]
+    outs = {}
+    for mode, extra in (("proc", []), ("thread", ["--in-process"])):
+        outs[mode] = str(tmp_path / mode)
+        r = subprocess.run(base + ["-O", outs[mode]] + extra, env=ENV, cwd=ROOT, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        assert re.search(r"Including chains", r.stdout)
+    assert "chain=2 status=done exit_code=0" in r.stdout
+    for i in range(3):
+        a, b = (os.path.join(outs[m], "chain_%d" % i) for m in ("proc", "thread"))
+        assert tree_names(a) == tree_names(b)
+        assert open(os.path.join(a, "random_seed.txt")).read() == open(os.path.join(b, "random_seed.txt")).read()
+        rows = open(os.path.join(b, "mcmc_samples.txt")).read().strip().split("\n")
+        assert len(rows) == 14
+    assert tree_names(outs["proc"]) == tree_names(outs["thread"])
+    assert not [f for f in os.listdir(ROOT) if f in ("trees.zip", "mcmc_samples.txt", "random_seed.txt")]   # nothing leaks into cwd
