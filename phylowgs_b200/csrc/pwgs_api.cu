@@ -72,7 +72,8 @@ struct pwgs_ctx {
     DevBuf<double> w_lbc, w_mu_r;
     CnvWork work;
     // ---- MH
-    DevBuf<double> partials, ring, phi_out, pi_out, llh_out, scratch;
+    DevBuf<unsigned long long> sums;
+    DevBuf<double> ring, phi_out, pi_out, llh_out, scratch;
     DevBuf<unsigned long long> counter, prof;
     bool opt_prof = false;
     unsigned long long prof_host[16] = {0};
@@ -133,7 +134,7 @@ int pwgs_destroy(pwgs_ctx *c)
     c->phi.release(); c->pi.release(); c->coef.release();
     c->code_tmp.release(); c->enode_tmp.release(); c->pos.release(); c->w_a.release(); c->w_d.release(); c->w_code.release();
     c->w_enode.release(); c->overflow.release(); c->ecoef_tmp.release(); c->w_ecoef.release(); c->w_lbc.release(); c->w_mu_r.release();
-    c->partials.release(); c->ring.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
+    c->sums.release(); c->ring.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
     c->counter.release(); c->prof.release(); c->acc_out.release(); c->abort_flag.release(); c->cols.release(); c->rows.release(); c->plist.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -413,7 +414,8 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     const size_t stage_bytes = mh_stage_bytes((c->Dp + cpc - 1) / cpc, c->work.cchunk, c->T, c->work.Emax) + 16;
     const int stage = (c->opt_stage && smem + stage_bytes <= 224 * 1024) ? 1 : 0;
     if (stage) smem += stage_bytes;
-    CUDA_TRY(c->partials.alloc((size_t)2 * PWGS_MAX_BATCH * cpc));
+    CUDA_TRY(c->sums.alloc((size_t)2 * PWGS_MAX_BATCH * MH_SUM_STRIDE));
+    CUDA_TRY(cudaMemsetAsync(c->sums.p, 0, (size_t)2 * PWGS_MAX_BATCH * MH_SUM_STRIDE * sizeof(unsigned long long), c->stream));
     CUDA_TRY(c->ring.alloc((size_t)(MH_RING + 2) * mh_bufstride(c->K, c->T, B)));   // ring + the two epoch slots
     const int distributed = c->opt_dist < 0 ? (cpc >= MH_DIST_MIN_CTAS ? 1 : 0) : c->opt_dist;
     CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
@@ -437,7 +439,7 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     p.phi_out = c->phi_out.p; p.pi_out = c->pi_out.p; p.acc_out = c->acc_out.p; p.llh_out = c->llh_out.p;
     p.iters = iters; p.max_batch = B; p.stage = stage; p.distributed = distributed; p.mh_std = (double)(float)mh_std;   // mh.hpp:28: MH_STD is a float
     p.seed = seed; p.stream = stream;
-    p.partials = c->partials.p; p.ring = c->ring.p; p.counter = c->counter.p; p.abort_flag = c->abort_flag.p;
+    p.sums = c->sums.p; p.ring = c->ring.p; p.counter = c->counter.p; p.abort_flag = c->abort_flag.p;
     p.lbc_plain_sum = c->lbc_plain_sum; p.log_tiny = kLogTinyMh;
     p.prof = nullptr;
     if (c->opt_prof) { CUDA_TRY(c->prof.alloc(16)); p.prof = c->prof.p; }

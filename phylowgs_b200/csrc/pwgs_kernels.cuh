@@ -340,6 +340,7 @@ __global__ void collapse_kernel(int Dp, int T, int C, const int *__restrict__ pa
 #define MH_BU 4                          // proposals evaluated per thread in one pass over its data
 #define MH_RING 4                        // slots of the global proposal ring
 #define MH_WATCHDOG_CYCLES 8000000000ll  // ~4 s of SM clock: a barrier that has not completed by then never will
+#define MH_SUM_STRIDE 16                 // 64-bit words between the running totals of two proposals: one L2 line each
 #define MH_DIST_MIN_CTAS 32              // chains with fewer CTAs draw every proposal locally in every CTA
 
 struct MhParams {
@@ -361,7 +362,8 @@ struct MhParams {
     int distributed;                    // 1: proposals two batches ahead are drawn once per chain and shared through `ring`
     double mh_std;
     unsigned long long seed, stream;
-    double *partials;                   // [2][PWGS_MAX_BATCH][cpc]
+    unsigned long long *sums;           // [2][PWGS_MAX_BATCH][MH_SUM_STRIDE] running fixed-point totals of the CTAs' partial sums: words 0, 1
+                                        // of each proposal's own 128-byte line (atomics to one line serialise in L2); zeroed before launch
     double *ring;                       // [MH_RING][bufstride] proposal ring (distributed mode)
     unsigned long long *counter;        // arrival counter of the chain's grid barrier (zeroed before launch)
     int *abort_flag;                    // watchdog: set when a spin wait exceeds MH_WATCHDOG_CYCLES; every CTA then leaves the loop
@@ -389,6 +391,7 @@ struct MhSmem {
     __device__ __forceinline__ double *logr(int b) const { return buf0 + b * bufstride + o_logr; }
     double *red;                                    // [nb][warps per proposal group]: per-warp sums of the current batch
     double *llh;                                    // [MAXB]
+    unsigned long long *seen;                       // [2][MAXB][2]: p.sums as of the last time this CTA read each parity
     double *pscratch;                               // [MH_CWARPS+1][2K] per warp: pi1 and phi1 of a proposal drawn for the ring
     volatile int *ctl;                              // producer mailbox, see MhCtl
     int *tin, *tout;                                // [K]
@@ -400,7 +403,7 @@ __host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
 {
     size_t KT = (size_t)K * T;
     const size_t red = (size_t)maxb > MH_BU * MH_GWARPS ? (size_t)maxb : MH_BU * MH_GWARPS;
-    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 2 * (size_t)K * (MH_CWARPS + 1);
+    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 4 * (size_t)maxb + 2 * (size_t)K * (MH_CWARPS + 1);
 }
 __host__ __device__ inline size_t mh_smem_ints(int K) { return CTL_WORDS + 2 * (size_t)K; }
 
@@ -864,6 +867,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = MAXB * KT; S.o_hast = 2 * MAXB * KT; S.o_logr = 2 * MAXB * KT + MAXB * T;
         S.buf0 = q; q += 2 * S.bufstride;
         S.red = q; q += (MAXB > MH_BU * MH_GWARPS ? MAXB : MH_BU * MH_GWARPS); S.llh = q; q += MAXB;
+        S.seen = (unsigned long long *)q; q += 4 * MAXB;
         S.pscratch = q; q += 2 * K * (MH_CWARPS + 1);
         S.ctl = (volatile int *)q; S.tin = (int *)q + CTL_WORDS; S.tout = S.tin + K;
     }
@@ -875,6 +879,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
     }
     for (int k = tid; k < K; k += MH_THREADS) { S.tin[k] = p.tin[k]; S.tout[k] = p.tout[k]; }
     if (tid < CTL_WORDS) S.ctl[tid] = 0;
+    for (int i = tid; i < 4 * MAXB; i += MH_THREADS) S.seen[i] = 0ull;
 
     // this CTA's slices of the plain work list (contiguous) and of the CNV work list (already CTA-major)
     const int pchunk = (p.Dp + cpc - 1) / cpc, p0 = min(p.Dp, rank * pchunk), p1 = min(p.Dp, p0 + pchunk);
@@ -983,10 +988,16 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         // ---------------- publish the CTA's partial sums and arrive at the chain barrier (release)
         const int parity = g & 1;
         if (warp == 0) {
+            // The CTA's partial sum t goes into the chain's running totals as two integers, rint(t) and the remainder in
+            // units of 2^-52: integer adds commute, so every CTA later reads the same bits whatever order the adds landed in,
+            // and the total is exact (no rounding between CTAs).  The totals are never reset: readers take differences.
+            unsigned long long *acc = p.sums + (size_t)parity * MH_SUM_STRIDE * PWGS_MAX_BATCH;
             for (int b = lane; b < b_nb; b += 32) {
                 double t = 0.0;
                 for (int r = 0; r < wpg; r++) t += S.red[b * wpg + r];
-                p.partials[((size_t)parity * PWGS_MAX_BATCH + b) * cpc + rank] = t;
+                const double th = rint(t);
+                atomicAdd(acc + MH_SUM_STRIDE * b, (unsigned long long)(long long)th);
+                atomicAdd(acc + MH_SUM_STRIDE * b + 1, (unsigned long long)__double2ll_rn((t - th) * 4503599627370496.0));
             }
             __syncwarp();
             if (lane == 0) {
@@ -1022,7 +1033,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         if (S.ctl[CTL_ABORT]) break;
         MH_PROF(3);
 
-        // ---------------- every CTA sums the same partials in the same order -> bit-identical decisions everywhere;
+        // ---------------- every CTA reads the same integer totals -> bit-identical decisions everywhere;
         // the loads of the next batch's ring slot (complete: every CTA posted its share before arriving) go out first so that
         // all L2 round trips of this step overlap
         const bool fetch = !next_local && n1_nb > 0;
@@ -1033,29 +1044,12 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
             if (tid < n1_nb * T) f_h = __ldcg(slot + S.o_hast + tid);
             if (tid < n1_nb) f_r = __ldcg(slot + S.o_logr + tid);
         }
-        {
-            const double *pp = p.partials + (size_t)parity * PWGS_MAX_BATCH * cpc;
-            const int rot = (rank * 13) & (b_nb - 1);                           // CTAs walk the proposals in rotated order so that the
-#pragma unroll 1
-            for (int bq = warp; bq < b_nb; bq += 2 * MH_CWARPS) {                // chain does not hammer the same L2 lines at once
-                const int b0 = (bq + rot) & (b_nb - 1), b1 = bq + MH_CWARPS < b_nb ? ((bq + MH_CWARPS + rot) & (b_nb - 1)) : b_nb;
-                double v0[5], v1[5];
-#pragma unroll
-                for (int i = 0; i < 5; i++) {
-                    const int r = lane + 32 * i;
-                    v0[i] = (r < cpc) ? __ldcg(pp + (size_t)b0 * cpc + r) : 0.0;
-                    v1[i] = (b1 < b_nb && r < cpc) ? __ldcg(pp + (size_t)b1 * cpc + r) : 0.0;
-                }
-                double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-                for (int i = 0; i < 5; i++) { t0 += v0[i]; t1 += v1[i]; }
-                for (int r = lane + 160; r < cpc; r += 32) {                     // chains wider than 160 CTAs (not on B200)
-                    t0 += __ldcg(pp + (size_t)b0 * cpc + r);
-                    if (b1 < b_nb) t1 += __ldcg(pp + (size_t)b1 * cpc + r);
-                }
-                t0 = warp_sum(t0); t1 = warp_sum(t1);
-                if (lane == 0) { S.llh[b0] = t0; if (b1 < b_nb) S.llh[b1] = t1; }
-            }
+        if (tid < MAXB) {                              // the batch's totals = what was added to this parity since we last looked
+            const ulonglong2 now = __ldcg((const ulonglong2 *)(p.sums + ((size_t)parity * PWGS_MAX_BATCH + tid) * MH_SUM_STRIDE));
+            unsigned long long *sn = S.seen + (size_t)parity * 2 * MAXB + 2 * tid;
+            const unsigned long long was_x = sn[0], was_y = sn[1];
+            sn[0] = now.x; sn[1] = now.y;
+            S.llh[tid] = (double)(long long)(now.x - was_x) + (double)(long long)(now.y - was_y) * 2.220446049250313e-16;
         }
         if (fetch) {
             double *dst = S.prop_pi(cur ^ 1);
