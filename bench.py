@@ -279,6 +279,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config3")
     ap.add_argument("--mh-batch", type=int, default=0, help="speculative proposals per grid barrier (0 = library default)")
+    ap.add_argument("--round-weights", default="", help="tuning: relative cost of a warp round 'plain,cnv1,cnv2,cnv3' for the work "
+                                                        "partition (default: the library's)")
     ap.add_argument("--cpu-sample-iters", type=int, default=400, help="MH iterations of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mh-std", type=float, default=MH_STD, help="proposal concentration (evolve.py adapts it between 100 and 10000)")
@@ -346,6 +348,9 @@ def main():
     eng.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
     if args.mh_batch:
         eng.set_option("mh_batch", args.mh_batch)
+    if args.round_weights:
+        for name, v in zip(("mh_w_plain", "mh_w_cnv1", "mh_w_cnv2", "mh_w_cnv3"), args.round_weights.split(",")):
+            eng.set_option(name, int(v))
     if args.profile_phases:
         eng.set_option("mh_profile", 1)
     stats = [eng.get_option(n) for n in ("cnv_nu1", "cnv_nu2", "cnv_nu3", "cnv_entry_states")]
@@ -409,6 +414,10 @@ def main():
         tot = max(sum(pc[:7]), 1)
         print("phase cycles (CTA 0, last launch): " + ", ".join("%s=%d (%.1f%%)" % (n, v, 100.0 * v / tot) for n, v in zip(names[:7], pc[:7]))
               + ", batches=%d, cycles/batch=%.0f" % (pc[7], tot / max(pc[7], 1)), file=sys.stderr)
+        lo, hi, sm = (eng.get_option("mh_lik_" + k) for k in ("min", "max", "sum"))
+        ncta = eng.get_option("mh_ctas") or eng.get_option("n_sms")
+        print("likelihood cycles over the chain's CTAs: min %d  mean %.0f  max %d  (max/mean %.3f)" % (lo, sm / ncta, hi, hi * ncta / max(sm, 1)),
+              file=sys.stderr)
     # ---- opt-in fast path, reported separately (not the headline): plain data through exact integer totals (K0d)
     collapsed = None
     if eng.get_option("n_classes") > 0:

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <queue>
+#include <functional>
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -65,9 +67,13 @@ struct pwgs_ctx {
     DevBuf<double> phi, pi;
     DevBuf<int4> coef;                                    // dense [K][M] coefficients, built only for pwgs_get_data_states
     // sparse CNV work list of the MH kernel (rebuilt lazily after set_tree / when the CTA count changes)
-    int maxL = 0, work_cpc = -1;
+    int maxL = 0, work_cpc = -1, work_collapse = -1;
+    int pchunk = 0;
+    std::vector<int> plan_counts;                // [cpc][4] rounds per CTA: plain thirds, CNV rounds with 1 / 2 / 3 states (diagnostics)
+    const int *pstart_dev = nullptr;
+    int opt_w[4] = {100, 160, 400, 640};             // relative cost of a warp round: plain, CNV-affected with 1 / 2 / 3 merged states
     bool work_valid = false;
-    DevBuf<int> code_tmp, enode_tmp, pos, w_a, w_d, w_code, w_enode, overflow;
+    DevBuf<int> code_tmp, enode_tmp, pos, w_a, w_d, w_code, w_enode, overflow, plan;
     DevBuf<int4> ecoef_tmp, w_ecoef;
     DevBuf<double> w_lbc, w_mu_r;
     CnvWork work;
@@ -76,7 +82,8 @@ struct pwgs_ctx {
     DevBuf<double> ring, phi_out, pi_out, llh_out, scratch;
     DevBuf<unsigned long long> counter, prof;
     bool opt_prof = false;
-    unsigned long long prof_host[16] = {0};
+    unsigned long long prof_host[16 + 256] = {0};
+    int prof_cpc = 0;
     DevBuf<int> acc_out, rows, cols, abort_flag;
     DevBuf<MhParams> plist;
     int opt_batch = PWGS_MAX_BATCH, opt_ctas = 0, opt_stage = 1, opt_dist = -1;
@@ -133,7 +140,7 @@ int pwgs_destroy(pwgs_ctx *c)
     c->parent.release(); c->depth.release(); c->tin.release(); c->tout.release(); c->order.release(); c->node_of_datum.release();
     c->phi.release(); c->pi.release(); c->coef.release();
     c->code_tmp.release(); c->enode_tmp.release(); c->pos.release(); c->w_a.release(); c->w_d.release(); c->w_code.release();
-    c->w_enode.release(); c->overflow.release(); c->ecoef_tmp.release(); c->w_ecoef.release(); c->w_lbc.release(); c->w_mu_r.release();
+    c->w_enode.release(); c->overflow.release(); c->plan.release(); c->ecoef_tmp.release(); c->w_ecoef.release(); c->w_lbc.release(); c->w_mu_r.release();
     c->sums.release(); c->ring.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
     c->counter.release(); c->prof.release(); c->acc_out.release(); c->abort_flag.release(); c->cols.release(); c->rows.release(); c->plist.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -352,40 +359,136 @@ int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node
 
 } // extern "C"
 
-// ------------------------------------------------------------------ sparse CNV work list (K0c)
-static int prepare_cnv_work(pwgs_ctx *c, int cpc)
+// ------------------------------------------------------------------ sparse CNV work list (K0c) and the chain's work partition
+// The MH kernel walks its data one warp round (32 data, one per lane) at a time and a round costs what its most expensive lane
+// costs.  So the unit of the partition is the round: the CNV-affected SSMs, sorted by their number of merged states, are cut
+// into rounds of 32, the plain data likewise, and whole rounds are dealt to the CTAs longest-processing-time-first (each
+// round to the least loaded CTA).  Every CTA's lists are then multiples of 32 -- no partially filled rounds but the single
+// tail of each list -- and the loads differ by less than one plain round.  (Dealing SSMs one by one gave every CTA a
+// 5/32-filled and a mixed-state round: 80 % lane efficiency at config 3.)
+struct Partition {
+    std::vector<int> round_slot, cta_nc, pstart, counts;
+    int cchunk = 0, pchunk = 0;
+};
+static Partition plan_partition(int cpc, int M, const int n_states[3] /* SSMs with 3, 2, 1 states */, int Dp_units_of, const int w[4])
 {
-    if (c->work_valid && c->work_cpc == cpc) return PWGS_OK;
+    Partition P;
+    const int U = (M + 31) / 32, PU = (Dp_units_of + 31) / 32;
+    P.counts.assign((size_t)cpc * 4, 0);
+    std::vector<int> n_cnv(cpc, 0);
+    typedef std::pair<long long, int> Slot;
+    std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> heap;
+    for (int i = 0; i < cpc; i++) heap.push(Slot(0, i));
+    std::vector<int> owner(U, 0), local(U, 0);
+    for (int u = 0; u < U; u++) {                                         // rounds in sorted order = most expensive first
+        const int r = 32 * u, cls = r < n_states[0] ? 3 : (r < n_states[0] + n_states[1] ? 2 : 1);
+        Slot t = heap.top(); heap.pop();
+        owner[u] = t.second; local[u] = n_cnv[t.second]++;
+        P.counts[(size_t)t.second * 4 + cls]++;
+        heap.push(Slot(t.first + w[cls], t.second));
+    }
+    // plain rounds in thirds: a full batch gives every warp three proposal groups (classes 0, 1, 2), and each class has its own
+    // partition of the plain list, so a CTA can take a round for one or two of the classes only.  n3[c] = thirds of CTA c
+    // (levelled like the rounds above, loads in units of a third of a weight); with S = running sum of n3, class i's boundary
+    // after CTA c is floor((S + i) / 3) rounds: monotone, ending at PU for every class, and the three classes' counts of a CTA
+    // add up to n3[c] exactly (Hermite's identity).  The three ranges of a CTA differ by at most one round at either end.
+    {
+        // identical units: water-filling in closed form instead of 3*PU heap operations.  Loads in units of w/3.
+        std::vector<long long> L(cpc, 0);
+        while (!heap.empty()) { Slot t = heap.top(); heap.pop(); L[t.second] = 3 * t.first; }
+        const long long N = 3LL * PU, wq = w[0];
+        std::vector<int> n3(cpc, 0);
+        if (N > 0) {
+            long long lo = *std::min_element(L.begin(), L.end()), hi = *std::max_element(L.begin(), L.end()) + wq * (N / cpc + 2);
+            auto filled = [&](long long lam) { long long t = 0; for (int c = 0; c < cpc; c++) if (lam > L[c]) t += (lam - L[c] + wq - 1) / wq; return t; };
+            while (lo < hi) {                                             // smallest level whose fill covers N units
+                const long long mid = lo + (hi - lo) / 2;
+                if (filled(mid) >= N) hi = mid; else lo = mid + 1;
+            }
+            long long total = 0;
+            for (int c = 0; c < cpc; c++) { n3[c] = lo > L[c] ? (int)((lo - L[c] + wq - 1) / wq) : 0; total += n3[c]; }
+            // give back the surplus where the last unit started highest (what the greedy would have dealt last)
+            std::vector<std::pair<long long, int>> last;
+            for (int c = 0; c < cpc; c++) if (n3[c] > 0) last.push_back(std::make_pair(L[c] + (n3[c] - 1) * wq, c));
+            std::sort(last.begin(), last.end(), std::greater<std::pair<long long, int>>());
+            for (size_t k = 0; k < last.size() && total > N; k++) { n3[last[k].second]--; total--; }
+        }
+        for (int c = 0; c < cpc; c++) P.counts[(size_t)c * 4] = n3[c];
+        P.pstart.assign((size_t)MH_PCLASSES * (cpc + 1), 0);
+        long long S = 0;
+        int maxp = 0;
+        for (int c = 0; c < cpc; c++) {
+            S += n3[c];
+            int lo = Dp_units_of, hi = 0;
+            for (int i = 0; i < MH_PCLASSES; i++) {
+                const int e = (int)std::min<long long>(Dp_units_of, 32 * ((S + i) / 3));
+                P.pstart[(size_t)i * (cpc + 1) + c + 1] = e;
+                lo = std::min(lo, P.pstart[(size_t)i * (cpc + 1) + c]); hi = std::max(hi, e);
+            }
+            maxp = std::max(maxp, hi - lo);
+        }
+        P.pchunk = maxp;
+    }
+    int maxc = 0;
+    for (int i = 0; i < cpc; i++) maxc = std::max(maxc, n_cnv[i]);
+    P.cchunk = 32 * maxc;
+    P.round_slot.resize(std::max(U, 1));
+    for (int u = 0; u < U; u++) P.round_slot[u] = owner[u] * P.cchunk + 32 * local[u];
+    P.cta_nc.resize(cpc);
+    for (int i = 0; i < cpc; i++) P.cta_nc[i] = 32 * n_cnv[i];
+    if (U > 0 && M % 32) P.cta_nc[owner[U - 1]] -= 32 - M % 32;          // the tail round is the last (cheapest) one of its CTA
+    return P;
+}
+
+static int prepare_cnv_work(pwgs_ctx *c, int cpc, int collapse)
+{
+    if (c->work_valid && c->work_cpc == cpc && c->work_collapse == collapse) return PWGS_OK;
     const int M = c->M, T = c->T, K = c->K;
     CnvWork &w = c->work;
     w.Emax = std::max(1, std::min(K, c->maxL + 2));
-    w.cchunk = (M + cpc - 1) / cpc;
-    w.Mp = std::max(1, w.cchunk * cpc);
     cudaStream_t s = c->stream;
+    int h[4] = {0, 0, 0, 0};                                             // overflow flag, SSMs with 3 / 2 / 1 merged states
+    if (M > 0) {
+        CUDA_TRY(c->code_tmp.alloc(M)); CUDA_TRY(c->pos.alloc(M)); CUDA_TRY(c->overflow.alloc(4));
+        CUDA_TRY(c->enode_tmp.alloc((size_t)M * w.Emax)); CUDA_TRY(c->ecoef_tmp.alloc((size_t)M * w.Emax));
+        CUDA_TRY(cudaMemsetAsync(c->overflow.p, 0, 4 * sizeof(int), s));
+        cnv_sparse_kernel<<<(M + 127) / 128, 128, 0, s>>>(data_view(c), tree_view(c), M, w.Emax, c->cidx.p, c->code_tmp.p, c->enode_tmp.p,
+                                                          c->ecoef_tmp.p, c->overflow.p);
+        CUDA_TRY(cudaGetLastError());
+        cnv_sort_kernel<<<1, 1024, 0, s>>>(M, c->code_tmp.p, c->pos.p, c->overflow.p + 1);
+        CUDA_TRY(cudaGetLastError());
+        c->n_launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(h, c->overflow.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (h[0]) return fail(PWGS_ELIMIT, "internal: sparse CNV entry bound exceeded");
+    }
+    const Partition P = plan_partition(cpc, M, h + 1, collapse ? 0 : c->Dp, c->opt_w);
+    w.cchunk = P.cchunk;
+    w.Mp = std::max(1, w.cchunk * cpc);
+    c->pchunk = P.pchunk;
+    c->plan_counts = P.counts;
+    // one upload: [round_slot | cta_nc | pstart]
+    std::vector<int> tab(P.round_slot);
+    tab.insert(tab.end(), P.cta_nc.begin(), P.cta_nc.end());
+    tab.insert(tab.end(), P.pstart.begin(), P.pstart.end());
+    CUDA_TRY(c->plan.alloc(tab.size()));
+    CUDA_TRY(cudaMemcpyAsync(c->plan.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));   // pageable: staged before return
+    const int *d_round_slot = c->plan.p, *d_cta_nc = c->plan.p + P.round_slot.size();
+    c->pstart_dev = d_cta_nc + cpc;                                      // [MH_PCLASSES][cpc+1]
     CUDA_TRY(c->w_a.alloc((size_t)w.Mp * T)); CUDA_TRY(c->w_d.alloc((size_t)w.Mp * T)); CUDA_TRY(c->w_lbc.alloc((size_t)w.Mp * T));
     CUDA_TRY(c->w_mu_r.alloc(w.Mp)); CUDA_TRY(c->w_code.alloc(w.Mp));
     CUDA_TRY(c->w_enode.alloc((size_t)w.Mp * w.Emax)); CUDA_TRY(c->w_ecoef.alloc((size_t)w.Mp * w.Emax));
     w.a = c->w_a.p; w.d = c->w_d.p; w.lbc = c->w_lbc.p; w.mu_r = c->w_mu_r.p; w.code = c->w_code.p; w.enode = c->w_enode.p; w.ecoef = c->w_ecoef.p;
+    w.cta_nc = d_cta_nc;
     if (M > 0) {
-        CUDA_TRY(c->code_tmp.alloc(M)); CUDA_TRY(c->pos.alloc(M)); CUDA_TRY(c->overflow.alloc(1));
-        CUDA_TRY(c->enode_tmp.alloc((size_t)M * w.Emax)); CUDA_TRY(c->ecoef_tmp.alloc((size_t)M * w.Emax));
-        CUDA_TRY(cudaMemsetAsync(c->overflow.p, 0, sizeof(int), s));
-        cnv_sparse_kernel<<<(M + 127) / 128, 128, 0, s>>>(data_view(c), tree_view(c), M, w.Emax, c->cidx.p, c->code_tmp.p, c->enode_tmp.p,
-                                                          c->ecoef_tmp.p, c->overflow.p);
-        CUDA_TRY(cudaGetLastError());
-        cnv_sort_kernel<<<1, 1024, 0, s>>>(M, c->code_tmp.p, c->pos.p);
-        CUDA_TRY(cudaGetLastError());
-        cnv_scatter_kernel<<<(M + 127) / 128, 128, 0, s>>>(M, T, cpc, w, c->pos.p, c->ca.p, c->cd.p, c->clbc.p, c->cmu_r.p, c->code_tmp.p,
+        cnv_scatter_kernel<<<(M + 127) / 128, 128, 0, s>>>(M, T, d_round_slot, w, c->pos.p, c->ca.p, c->cd.p, c->clbc.p, c->cmu_r.p, c->code_tmp.p,
                                                            c->enode_tmp.p, c->ecoef_tmp.p);
         CUDA_TRY(cudaGetLastError());
-        c->n_launches += 3;
-        int ovf = 0;
-        CUDA_TRY(cudaMemcpyAsync(&ovf, c->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        if (ovf) return fail(PWGS_ELIMIT, "internal: sparse CNV entry bound exceeded");
+        c->n_launches += 1;
     }
     c->work_valid = true;
     c->work_cpc = cpc;
+    c->work_collapse = collapse;
     return PWGS_OK;
 }
 
@@ -409,9 +512,10 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     size_t smem = mh_smem_bytes(c->K, c->T, B);
     while (smem > 160 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B); }
     if (smem > 200 * 1024) return fail(PWGS_ELIMIT, "K*T too large for the shared-memory node table");
-    { int rc_ = prepare_cnv_work(c, cpc); if (rc_ != PWGS_OK) return rc_; }
+    const int collapse = (c->opt_collapse && c->n_classes > 0 && c->Dp > 0) ? c->n_classes : 0;
+    { int rc_ = prepare_cnv_work(c, cpc, collapse); if (rc_ != PWGS_OK) return rc_; }
     // stage each CTA's slice of the data in shared memory when it fits beside the node tables
-    const size_t stage_bytes = mh_stage_bytes((c->Dp + cpc - 1) / cpc, c->work.cchunk, c->T, c->work.Emax) + 16;
+    const size_t stage_bytes = mh_stage_bytes(c->pchunk, c->work.cchunk, c->T, c->work.Emax) + 16;
     const int stage = (c->opt_stage && smem + stage_bytes <= 224 * 1024) ? 1 : 0;
     if (stage) smem += stage_bytes;
     CUDA_TRY(c->sums.alloc((size_t)2 * PWGS_MAX_BATCH * MH_SUM_STRIDE));
@@ -421,7 +525,6 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->abort_flag.p, 0, sizeof(int), c->stream));
 
-    const int collapse = (c->opt_collapse && c->n_classes > 0 && c->Dp > 0) ? c->n_classes : 0;
     if (collapse) {
         const size_t n = (size_t)c->K * collapse * c->T * 2;
         CUDA_TRY(c->cl_sums.alloc(n));
@@ -435,6 +538,7 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     p.n_classes = collapse; p.cl_sums = c->cl_sums.p; p.cl_mu_r = c->cl_mu_r.p; p.cl_mu_v = c->cl_mu_v.p;
     p.pa = c->pa.p; p.pd = c->pd.p; p.pmu_r = c->pmu_r.p; p.pmu_v = c->pmu_v.p; p.pnode = c->pnode.p;
     p.cw = c->work;
+    p.pstart = c->pstart_dev; p.pchunk = c->pchunk;
     p.tin = c->tin.p; p.tout = c->tout.p; p.phi0 = c->phi.p; p.pi0 = c->pi.p;
     p.phi_out = c->phi_out.p; p.pi_out = c->pi_out.p; p.acc_out = c->acc_out.p; p.llh_out = c->llh_out.p;
     p.iters = iters; p.max_batch = B; p.stage = stage; p.distributed = distributed; p.mh_std = (double)(float)mh_std;   // mh.hpp:28: MH_STD is a float
@@ -442,7 +546,7 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     p.sums = c->sums.p; p.ring = c->ring.p; p.counter = c->counter.p; p.abort_flag = c->abort_flag.p;
     p.lbc_plain_sum = c->lbc_plain_sum; p.log_tiny = kLogTinyMh;
     p.prof = nullptr;
-    if (c->opt_prof) { CUDA_TRY(c->prof.alloc(16)); p.prof = c->prof.p; }
+    if (c->opt_prof) { CUDA_TRY(c->prof.alloc(16 + 256)); p.prof = c->prof.p; c->prof_cpc = std::min(cpc, 256); }
     // pageable source: the runtime stages the bytes before returning, so the stack object is safe
     CUDA_TRY(cudaMemcpyAsync(c->plist.p, &p, sizeof(p), cudaMemcpyHostToDevice, c->stream));
 
@@ -623,6 +727,10 @@ int pwgs_set_option(pwgs_ctx *c, const char *name, int64_t value)
         c->opt_stage = value != 0;
     } else if (n == "mh_profile") {
         c->opt_prof = value != 0;
+    } else if (n == "mh_w_plain" || n == "mh_w_cnv1" || n == "mh_w_cnv2" || n == "mh_w_cnv3") {
+        if (value < 1 || value > 1000000) return fail(PWGS_EINVAL, "round weights must be in 1..1000000");
+        c->opt_w[n == "mh_w_plain" ? 0 : n == "mh_w_cnv1" ? 1 : n == "mh_w_cnv2" ? 2 : 3] = (int)value;
+        c->work_valid = false;
     } else return fail(PWGS_EINVAL, "unknown option " + n);
     return PWGS_OK;
 }
@@ -636,7 +744,7 @@ static int cnv_work_stats(pwgs_ctx *c, int64_t out[4])
     if (c->M == 0) return PWGS_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     int cpc = c->opt_ctas > 0 ? std::min(c->opt_ctas, c->n_sms) : c->n_sms;
-    int rc = prepare_cnv_work(c, cpc);
+    int rc = prepare_cnv_work(c, cpc, (c->opt_collapse && c->n_classes > 0 && c->Dp > 0) ? c->n_classes : 0);
     if (rc != PWGS_OK) return rc;
     std::vector<int> code(c->M);
     CUDA_TRY(cudaMemcpyAsync(code.data(), c->code_tmp.p, sizeof(int) * c->M, cudaMemcpyDeviceToHost, c->stream));
@@ -668,6 +776,22 @@ int pwgs_get_option(pwgs_ctx *c, const char *name, int64_t *value)
     else if (n == "launches") *value = c->n_launches;
     else if (n == "n_classes") *value = c->n_classes;
     else if (n == "mh_collapse") *value = c->opt_collapse;
+    else if (n.rfind("mh_lik_cta_", 0) == 0) {
+        const int r = atoi(n.c_str() + 11);
+        if (r < 0 || r >= c->prof_cpc) return fail(PWGS_EINVAL, "no such CTA");
+        *value = (int64_t)c->prof_host[16 + r];
+    }
+    else if (n.rfind("mh_plan_", 0) == 0) {         // mh_plan_<class>_<cta>: rounds of class 0 (plain thirds) / 1..3 (CNV states) of a CTA
+        int cls = 0, r = 0;
+        if (sscanf(n.c_str() + 8, "%d_%d", &cls, &r) != 2 || cls < 0 || cls > 3 || r < 0 || (size_t)r * 4 + 3 >= c->plan_counts.size())
+            return fail(PWGS_EINVAL, "no such plan entry");
+        *value = c->plan_counts[(size_t)r * 4 + cls];
+    }
+    else if (n == "mh_lik_min" || n == "mh_lik_max" || n == "mh_lik_sum") {
+        unsigned long long mn = ~0ull, mx = 0, sm = 0;
+        for (int i = 0; i < c->prof_cpc; i++) { const unsigned long long v = c->prof_host[16 + i]; mn = std::min(mn, v); mx = std::max(mx, v); sm += v; }
+        *value = (int64_t)(n == "mh_lik_min" ? (c->prof_cpc ? mn : 0) : n == "mh_lik_max" ? mx : sm);
+    }
     else if (n.rfind("mh_prof_", 0) == 0 && n.size() == 9 && n[8] >= '0' && n[8] <= '9') *value = (int64_t)c->prof_host[n[8] - '0'];
     else if (n.rfind("mh_prof_1", 0) == 0 && n.size() == 10 && n[9] >= '0' && n[9] <= '5') *value = (int64_t)c->prof_host[10 + n[9] - '0'];
     else return fail(PWGS_EINVAL, "unknown option " + n);

@@ -166,7 +166,7 @@ __global__ void cnv_sparse_kernel(DataView dv, TreeView tv, int M, int Emax, con
 // Stable 3-bucket counting sort of the CNV-affected SSMs by their number of unique states, most expensive first (single CTA,
 // deterministic): pos[m] = rank of m in the sorted order.  Warps of the MH kernel then see (nearly) uniform work per round and
 // the partially filled last warp of a CTA holds the cheapest SSMs.
-__global__ void cnv_sort_kernel(int M, const int *__restrict__ code, int *__restrict__ pos)
+__global__ void cnv_sort_kernel(int M, const int *__restrict__ code, int *__restrict__ pos, int *__restrict__ counts)
 {
     __shared__ int cnt[1024][3];
     __shared__ int base[3];
@@ -180,14 +180,17 @@ __global__ void cnv_sort_kernel(int M, const int *__restrict__ code, int *__rest
         for (int i = 0; i < (int)blockDim.x; i++)
             for (int b = 0; b < 3; b++) { int v = cnt[i][b]; cnt[i][b] = run[b]; run[b] += v; }
         base[0] = 0; base[1] = run[0]; base[2] = run[0] + run[1];
+        counts[0] = run[0]; counts[1] = run[1]; counts[2] = run[2];     // SSMs with 3 / 2 / 1 merged states
     }
     __syncthreads();
     int o[3] = {base[0] + cnt[t][0], base[1] + cnt[t][1], base[2] + cnt[t][2]};
     for (int m = lo; m < hi; m++) pos[m] = o[3 - ((code[m] >> 8) & 3)]++;
 }
 
-// Scatter into the CTA-major layout the MH kernel streams: sorted rank r goes to CTA r % cpc, local slot r / cpc, i.e.
-// index (r % cpc) * cchunk + r / cpc, so every CTA gets the same mix of cheap and expensive SSMs, contiguous and sorted.
+// Scatter into the CTA-major layout the MH kernel streams.  The sorted list is cut into warp rounds of 32 consecutive SSMs
+// (uniform state count inside a round but for the two rounds straddling a class boundary); the host deals whole rounds to the
+// CTAs by cost (pwgs_api.cu: plan_partition) and passes round_slot[u] = first slot of round u: sorted rank r goes to
+// round_slot[r / 32] + r % 32.  A CTA's rounds are contiguous, most expensive first; it holds cta_nc[rank] SSMs.
 struct CnvWork {
     int *a, *d;            // [T][Mp]
     double *lbc;           // [T][Mp]
@@ -196,14 +199,15 @@ struct CnvWork {
     int *enode;            // [Emax][Mp]
     int4 *ecoef;           // [Emax][Mp]
     int Mp, cchunk, Emax;
+    const int *cta_nc;     // [cpc] CNV-affected SSMs of each CTA
 };
-__global__ void cnv_scatter_kernel(int M, int T, int cpc, CnvWork w, const int *__restrict__ pos, const int *__restrict__ ca,
+__global__ void cnv_scatter_kernel(int M, int T, const int *__restrict__ round_slot, CnvWork w, const int *__restrict__ pos, const int *__restrict__ ca,
                                    const int *__restrict__ cd, const double *__restrict__ clbc, const double *__restrict__ cmu_r,
                                    const int *__restrict__ code, const int *__restrict__ enode, const int4 *__restrict__ ecoef)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
-    const int r = pos[m], dst = (r % cpc) * w.cchunk + r / cpc;
+    const int r = pos[m], dst = round_slot[r >> 5] + (r & 31);
     for (int tp = 0; tp < T; tp++) {
         w.a[(size_t)tp * w.Mp + dst] = ca[(size_t)tp * M + m];
         w.d[(size_t)tp * w.Mp + dst] = cd[(size_t)tp * M + m];
@@ -341,6 +345,7 @@ __global__ void collapse_kernel(int Dp, int T, int C, const int *__restrict__ pa
 #define MH_RING 4                        // slots of the global proposal ring
 #define MH_WATCHDOG_CYCLES 8000000000ll  // ~4 s of SM clock: a barrier that has not completed by then never will
 #define MH_SUM_STRIDE 16                 // 64-bit words between the running totals of two proposals: one L2 line each
+#define MH_PCLASSES 3                    // proposal-group classes of the plain partition: a warp's 1st / 2nd / 3rd group of a full batch
 #define MH_DIST_MIN_CTAS 32              // chains with fewer CTAs draw every proposal locally in every CTA
 
 struct MhParams {
@@ -348,6 +353,9 @@ struct MhParams {
     const int *pa, *pd;                 // [T][Dp]  plain data (SSMs outside CNVs + CNV data), sample-major
     const double *pmu_r, *pmu_v;        // [Dp]
     const int *pnode;                   // [Dp] node index of each plain datum
+    const int *pstart;                  // [MH_PCLASSES][cpc+1] for proposal groups of class i (= group / MH_CWARPS), CTA r walks plain data
+                                        // pstart[i][r] .. pstart[i][r+1]-1: whole warp rounds, dealt by cost in thirds of a round
+    int pchunk;                         // largest plain slice of any CTA (union over the classes; stride of the staged copy)
     CnvWork cw;                         // CNV-affected SSMs: sorted, CTA-major sparse work list (K0c)
     int n_classes;                      // > 0: plain data enter through their per-(node, class, sample) totals (K0d)
     const unsigned long long *cl_sums;  // [K][n_classes][T][2] = {sum a, sum d-a}
@@ -368,7 +376,7 @@ struct MhParams {
     unsigned long long *counter;        // arrival counter of the chain's grid barrier (zeroed before launch)
     int *abort_flag;                    // watchdog: set when a spin wait exceeds MH_WATCHDOG_CYCLES; every CTA then leaves the loop
     double lbc_plain_sum, log_tiny;
-    unsigned long long *prof;           // optional [16] cycle counters of CTA 0 / thread 0 (NULL = off)
+    unsigned long long *prof;           // optional [16 + cpc]: cycle counters of CTA 0 / thread 0, then every CTA's likelihood cycles (NULL = off)
 };
 
 // ---- shared-memory carve-up of one CTA (doubles first, then ints, then the staged data slice)
@@ -396,7 +404,7 @@ struct MhSmem {
     volatile int *ctl;                              // producer mailbox, see MhCtl
     int *tin, *tout;                                // [K]
 };
-enum MhCtl { CTL_GEN = 0, CTL_DONE = 1, CTL_PROD_DONE = 2, CTL_ABORT = 3, CTL_JOB = 4 /* 2 x {state, it, nb} */, CTL_WORDS = 12 };
+enum MhCtl { CTL_GEN = 0, CTL_DONE = 1, CTL_PROD_DONE = 2, CTL_ABORT = 3, CTL_JOB = 4 /* 2 x {state, it, nb} */, CTL_PRANGE = 12 /* MH_PCLASSES x {first, count} */, CTL_WORDS = 20 };
 
 __host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return 2 * (size_t)maxb * K * T + (size_t)maxb * T + maxb; }
 __host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
@@ -585,8 +593,8 @@ __host__ __device__ inline size_t mh_stage_bytes(int pchunk, int cchunk, int T, 
 // the group's stride and accumulating BU sums, so that every load / int->fp64 conversion is shared by BU proposals and the BU
 // independent chains of logarithms overlap in the FP64 pipe.  Leaves red[bb][warp] = the warp's sum for proposal g*BU+bb.
 template <int BU, class Slice>
-__device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S, const Slice &sl, int cur, int wpg, int role, int g, int lane,
-                                              int rank, int cpc)
+__device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S, const Slice &sl, int cur, int wpg, int role, int g, int pcls,
+                                              int lane, int rank, int cpc)
 {
     // proposal group g (proposals g*BU .. g*BU+BU-1) is evaluated by wpg warps; this warp is number `role` of them
     const int T = p.T, KT = p.K * T;
@@ -698,10 +706,11 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
         }
     }
 
-    // ---- plain data (mh.hpp:86-89): SSMs outside CNVs and the CNV data themselves
+    // ---- plain data (mh.hpp:86-89): SSMs outside CNVs and the CNV data themselves; the slice depends on the group's class
+    const int pbeg = S.ctl[CTL_PRANGE + 2 * pcls], pend = pbeg + S.ctl[CTL_PRANGE + 2 * pcls + 1];
 #pragma unroll 1
-    for (int j = lt; j - lane < sl.np; j += tpg) {
-        const bool act = j < sl.np;
+    for (int j = pbeg + lt; j - lane < pend; j += tpg) {
+        const bool act = j < pend;
         const int jj = act ? j : 0;
         const double mu_r = sl.pmu_r(jj), mu_v = sl.pmu_v(jj);
         const int nodeT = sl.pnode(jj) * T;
@@ -878,13 +887,21 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         S.prop_phi(0)[i] = p.phi0[i];
     }
     for (int k = tid; k < K; k += MH_THREADS) { S.tin[k] = p.tin[k]; S.tout[k] = p.tout[k]; }
-    if (tid < CTL_WORDS) S.ctl[tid] = 0;
+    if (tid < CTL_PRANGE) S.ctl[tid] = 0;             // (the CTL_PRANGE words are written below)
     for (int i = tid; i < 4 * MAXB; i += MH_THREADS) S.seen[i] = 0ull;
 
-    // this CTA's slices of the plain work list (contiguous) and of the CNV work list (already CTA-major)
-    const int pchunk = (p.Dp + cpc - 1) / cpc, p0 = min(p.Dp, rank * pchunk), p1 = min(p.Dp, p0 + pchunk);
+    // this CTA's slices of the plain work list (contiguous) and of the CNV work list (already CTA-major); both are whole
+    // warp rounds, dealt so that the CTAs' costs (not their counts) are level
+    int p0 = p.pstart[rank], p1 = p.pstart[rank + 1];
+    for (int i = 1; i < MH_PCLASSES; i++) { p0 = min(p0, p.pstart[i * (cpc + 1) + rank]); p1 = max(p1, p.pstart[i * (cpc + 1) + rank + 1]); }
+    const int pchunk = p.pchunk;
+    if (tid < MH_PCLASSES) {                           // per class: first datum (relative to the staged slice) and count
+        const int b = p.pstart[tid * (cpc + 1) + rank], e = p.pstart[tid * (cpc + 1) + rank + 1];
+        S.ctl[CTL_PRANGE + 2 * tid] = b - p0;
+        S.ctl[CTL_PRANGE + 2 * tid + 1] = p.n_classes > 0 ? 0 : e - b;
+    }
     const CnvWork &cw = p.cw;
-    const int cbase = rank * cw.cchunk, np = p.n_classes > 0 ? 0 : p1 - p0, nc = (p.M - rank + cpc - 1) / cpc;
+    const int cbase = rank * cw.cchunk, np = p.n_classes > 0 ? 0 : p1 - p0, nc = cw.cta_nc[rank];
     typename std::conditional<STAGED, SliceShared, SliceGlobal>::type sl;
     if constexpr (STAGED) {
         // carve the staging area behind the node tables (16-byte aligned) and copy the slice once
@@ -937,7 +954,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
     mh_refresh_state(p, S, 0, tid, warp, lane);
     consumer_sync();
 
-    const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool prof = p.prof != nullptr && tid == 0;
     unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t_prev = clock64();
 #define MH_PROF(slot) do { if (prof) { long long t_ = clock64(); pc[slot] += (unsigned long long)(t_ - t_prev); t_prev = t_; } } while (0)
@@ -975,12 +992,15 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
             // sub-partitions (warp id % 4) in different groups
             if (warp < MH_GWARPS) {
                 const int gq = warp / wpg, role = (warp - gq * wpg + gq) % wpg;
-                if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, wpg, role, gq, lane, rank, cpc); else mh_likelihood<1>(p, S, sl, cur, wpg, role, gq, lane, rank, cpc);
+                if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, wpg, role, gq, 0, lane, rank, cpc); else mh_likelihood<1>(p, S, sl, cur, wpg, role, gq, 0, lane, rank, cpc);
             }
         } else {
+            // large batches: several groups per warp, in turn; a warp's i-th group is of class i (at most MH_PCLASSES: 128
+            // proposals = 32 groups over 11 warps), and each class has its own partition of the plain data over the CTAs
+            int pcls = 0;
 #pragma unroll 1
-            for (int gq = warp; gq < ngroups; gq += MH_CWARPS)                  // large batches: several groups per warp, in turn
-                mh_likelihood<MH_BU>(p, S, sl, cur, 1, 0, gq, lane, rank, cpc);
+            for (int gq = warp; gq < ngroups; gq += MH_CWARPS, pcls++)
+                mh_likelihood<MH_BU>(p, S, sl, cur, 1, 0, gq, pcls, lane, rank, cpc);
         }
         consumer_sync();
         MH_PROF(0);
@@ -1116,7 +1136,10 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         MH_PROF(6);
     }
     if (tid == 0) { __threadfence_block(); S.ctl[CTL_DONE] = 1; }
-    if (prof) for (int i = 0; i < 8; i++) p.prof[i] = pc[i];
+    if (prof) {
+        if (blockIdx.x == 0) for (int i = 0; i < 8; i++) p.prof[i] = pc[i];
+        p.prof[16 + rank] = pc[0];                      // every CTA's likelihood cycles: the balance of the work partition
+    }
 #undef MH_PROF
 
     if (rank == 0) {
