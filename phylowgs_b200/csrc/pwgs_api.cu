@@ -67,7 +67,7 @@ struct pwgs_ctx {
     DevBuf<double> phi, pi;
     DevBuf<int4> coef;                                    // dense [K][M] coefficients, built only for pwgs_get_data_states
     // sparse CNV work list of the MH kernel (rebuilt lazily after set_tree / when the CTA count changes)
-    int maxL = 0, work_cpc = -1, work_collapse = -1;
+    int maxL = 0, work_cpc = -1, work_collapse = -1, work_ncls = -1;
     int pchunk = 0;
     std::vector<int> plan_counts;                // [cpc][4] rounds per CTA: plain thirds, CNV rounds with 1 / 2 / 3 states (diagnostics)
     const int *pstart_dev = nullptr;
@@ -370,7 +370,8 @@ struct Partition {
     std::vector<int> round_slot, cta_nc, pstart, counts;
     int cchunk = 0, pchunk = 0;
 };
-static Partition plan_partition(int cpc, int M, const int n_states[3] /* SSMs with 3, 2, 1 states */, int Dp_units_of, const int w[4])
+static Partition plan_partition(int cpc, int M, const int n_states[3] /* SSMs with 3, 2, 1 states */, int Dp_units_of, const int w[4],
+                                int ncls /* proposal-group classes a full batch has: 1..MH_PCLASSES */)
 {
     Partition P;
     const int U = (M + 31) / 32, PU = (Dp_units_of + 31) / 32;
@@ -387,16 +388,17 @@ static Partition plan_partition(int cpc, int M, const int n_states[3] /* SSMs wi
         P.counts[(size_t)t.second * 4 + cls]++;
         heap.push(Slot(t.first + w[cls], t.second));
     }
-    // plain rounds in thirds: a full batch gives every warp three proposal groups (classes 0, 1, 2), and each class has its own
-    // partition of the plain list, so a CTA can take a round for one or two of the classes only.  n3[c] = thirds of CTA c
-    // (levelled like the rounds above, loads in units of a third of a weight); with S = running sum of n3, class i's boundary
-    // after CTA c is floor((S + i) / 3) rounds: monotone, ending at PU for every class, and the three classes' counts of a CTA
-    // add up to n3[c] exactly (Hermite's identity).  The three ranges of a CTA differ by at most one round at either end.
+    // plain rounds in fractions: a full batch gives every warp ncls proposal groups in turn (classes 0..ncls-1; three at 128
+    // proposals), and each class has its own partition of the plain list, so a CTA can take a round for some of the classes
+    // only.  n3[c] = fractions (1/ncls of a round) of CTA c, levelled like the rounds above with loads in units of 1/ncls of a
+    // weight; with S = running sum of n3, class i's boundary after CTA c is floor((S + i) / ncls) rounds: monotone, ending at PU
+    // for every class, and the classes' counts of a CTA add up to n3[c] exactly (Hermite's identity).  The ranges of a CTA
+    // differ by at most one round at either end.  Classes a full batch does not have share class 0's partition.
     {
         // identical units: water-filling in closed form instead of 3*PU heap operations.  Loads in units of w/3.
         std::vector<long long> L(cpc, 0);
-        while (!heap.empty()) { Slot t = heap.top(); heap.pop(); L[t.second] = 3 * t.first; }
-        const long long N = 3LL * PU, wq = w[0];
+        while (!heap.empty()) { Slot t = heap.top(); heap.pop(); L[t.second] = ncls * t.first; }
+        const long long N = (long long)ncls * PU, wq = w[0];
         std::vector<int> n3(cpc, 0);
         if (N > 0) {
             long long lo = *std::min_element(L.begin(), L.end()), hi = *std::max_element(L.begin(), L.end()) + wq * (N / cpc + 2);
@@ -421,7 +423,7 @@ static Partition plan_partition(int cpc, int M, const int n_states[3] /* SSMs wi
             S += n3[c];
             int lo = Dp_units_of, hi = 0;
             for (int i = 0; i < MH_PCLASSES; i++) {
-                const int e = (int)std::min<long long>(Dp_units_of, 32 * ((S + i) / 3));
+                const int e = (int)std::min<long long>(Dp_units_of, 32 * ((S + (i < ncls ? i : 0)) / ncls));
                 P.pstart[(size_t)i * (cpc + 1) + c + 1] = e;
                 lo = std::min(lo, P.pstart[(size_t)i * (cpc + 1) + c]); hi = std::max(hi, e);
             }
@@ -440,9 +442,17 @@ static Partition plan_partition(int cpc, int M, const int n_states[3] /* SSMs wi
     return P;
 }
 
-static int prepare_cnv_work(pwgs_ctx *c, int cpc, int collapse)
+// proposal-group classes of a full batch of B proposals: a warp's 1st, 2nd, 3rd group (see the large-batch loop of mh_kernel)
+static int mh_group_classes(int B)
 {
-    if (c->work_valid && c->work_cpc == cpc && c->work_collapse == collapse) return PWGS_OK;
+    // 128 proposals = 32 groups over 11 warps: a warp's 1st / 2nd / 3rd group; smaller caps cut their groups into shares of the
+    // data rounds (MH_UNITS units again) and use two classes of groups; tiny caps have a single group
+    return B >= MH_BU * MH_UNITS ? MH_PCLASSES : (B >= 2 * MH_BU ? 2 : 1);
+}
+
+static int prepare_cnv_work(pwgs_ctx *c, int cpc, int collapse, int ncls)
+{
+    if (c->work_valid && c->work_cpc == cpc && c->work_collapse == collapse && c->work_ncls == ncls) return PWGS_OK;
     const int M = c->M, T = c->T, K = c->K;
     CnvWork &w = c->work;
     w.Emax = std::max(1, std::min(K, c->maxL + 2));
@@ -462,7 +472,7 @@ static int prepare_cnv_work(pwgs_ctx *c, int cpc, int collapse)
         CUDA_TRY(cudaStreamSynchronize(s));
         if (h[0]) return fail(PWGS_ELIMIT, "internal: sparse CNV entry bound exceeded");
     }
-    const Partition P = plan_partition(cpc, M, h + 1, collapse ? 0 : c->Dp, c->opt_w);
+    const Partition P = plan_partition(cpc, M, h + 1, collapse ? 0 : c->Dp, c->opt_w, ncls);
     w.cchunk = P.cchunk;
     w.Mp = std::max(1, w.cchunk * cpc);
     c->pchunk = P.pchunk;
@@ -489,6 +499,7 @@ static int prepare_cnv_work(pwgs_ctx *c, int cpc, int collapse)
     c->work_valid = true;
     c->work_cpc = cpc;
     c->work_collapse = collapse;
+    c->work_ncls = ncls;
     return PWGS_OK;
 }
 
@@ -513,7 +524,7 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     while (smem > 160 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B); }
     if (smem > 200 * 1024) return fail(PWGS_ELIMIT, "K*T too large for the shared-memory node table");
     const int collapse = (c->opt_collapse && c->n_classes > 0 && c->Dp > 0) ? c->n_classes : 0;
-    { int rc_ = prepare_cnv_work(c, cpc, collapse); if (rc_ != PWGS_OK) return rc_; }
+    { int rc_ = prepare_cnv_work(c, cpc, collapse, mh_group_classes(B)); if (rc_ != PWGS_OK) return rc_; }
     // stage each CTA's slice of the data in shared memory when it fits beside the node tables
     const size_t stage_bytes = mh_stage_bytes(c->pchunk, c->work.cchunk, c->T, c->work.Emax) + 16;
     const int stage = (c->opt_stage && smem + stage_bytes <= 224 * 1024) ? 1 : 0;
@@ -538,7 +549,7 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     p.n_classes = collapse; p.cl_sums = c->cl_sums.p; p.cl_mu_r = c->cl_mu_r.p; p.cl_mu_v = c->cl_mu_v.p;
     p.pa = c->pa.p; p.pd = c->pd.p; p.pmu_r = c->pmu_r.p; p.pmu_v = c->pmu_v.p; p.pnode = c->pnode.p;
     p.cw = c->work;
-    p.pstart = c->pstart_dev; p.pchunk = c->pchunk;
+    p.pstart = c->pstart_dev; p.pchunk = c->pchunk; p.ncls = c->work_ncls;
     p.tin = c->tin.p; p.tout = c->tout.p; p.phi0 = c->phi.p; p.pi0 = c->pi.p;
     p.phi_out = c->phi_out.p; p.pi_out = c->pi_out.p; p.acc_out = c->acc_out.p; p.llh_out = c->llh_out.p;
     p.iters = iters; p.max_batch = B; p.stage = stage; p.distributed = distributed; p.mh_std = (double)(float)mh_std;   // mh.hpp:28: MH_STD is a float
@@ -744,7 +755,7 @@ static int cnv_work_stats(pwgs_ctx *c, int64_t out[4])
     if (c->M == 0) return PWGS_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     int cpc = c->opt_ctas > 0 ? std::min(c->opt_ctas, c->n_sms) : c->n_sms;
-    int rc = prepare_cnv_work(c, cpc, (c->opt_collapse && c->n_classes > 0 && c->Dp > 0) ? c->n_classes : 0);
+    int rc = prepare_cnv_work(c, cpc, (c->opt_collapse && c->n_classes > 0 && c->Dp > 0) ? c->n_classes : 0, c->work_ncls > 0 ? c->work_ncls : mh_group_classes(c->opt_batch));
     if (rc != PWGS_OK) return rc;
     std::vector<int> code(c->M);
     CUDA_TRY(cudaMemcpyAsync(code.data(), c->code_tmp.p, sizeof(int) * c->M, cudaMemcpyDeviceToHost, c->stream));
@@ -781,6 +792,7 @@ int pwgs_get_option(pwgs_ctx *c, const char *name, int64_t *value)
         if (r < 0 || r >= c->prof_cpc) return fail(PWGS_EINVAL, "no such CTA");
         *value = (int64_t)c->prof_host[16 + r];
     }
+    else if (n == "mh_plan_classes") *value = c->work_ncls;
     else if (n.rfind("mh_plan_", 0) == 0) {         // mh_plan_<class>_<cta>: rounds of class 0 (plain thirds) / 1..3 (CNV states) of a CTA
         int cls = 0, r = 0;
         if (sscanf(n.c_str() + 8, "%d_%d", &cls, &r) != 2 || cls < 0 || cls > 3 || r < 0 || (size_t)r * 4 + 3 >= c->plan_counts.size())

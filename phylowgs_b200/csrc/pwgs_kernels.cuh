@@ -338,7 +338,7 @@ __global__ void collapse_kernel(int Dp, int T, int C, const int *__restrict__ pa
 // ============================================================================ K1
 #define MH_CWARPS 11                     // consumer warps (likelihood + bookkeeping); with the producer warp that is 12 warps = 3 per
                                          // SM sub-partition, the most that fit at 168 registers (8 interleaved chains of fp64 logarithms per thread)
-#define MH_GWARPS 8                      // of which this many (a power of two) share the proposal groups of a small batch
+#define MH_UNITS 32                      // work units (proposal group x share of the data rounds) a batch is cut into: ~3 per consumer warp
 #define MH_CONSUMERS (MH_CWARPS * 32)
 #define MH_THREADS (MH_CONSUMERS + 32)   // + one producer warp (proposal draws for the ring)
 #define MH_BU 4                          // proposals evaluated per thread in one pass over its data
@@ -353,9 +353,10 @@ struct MhParams {
     const int *pa, *pd;                 // [T][Dp]  plain data (SSMs outside CNVs + CNV data), sample-major
     const double *pmu_r, *pmu_v;        // [Dp]
     const int *pnode;                   // [Dp] node index of each plain datum
-    const int *pstart;                  // [MH_PCLASSES][cpc+1] for proposal groups of class i (= group / MH_CWARPS), CTA r walks plain data
+    const int *pstart;                  // [MH_PCLASSES][cpc+1] for proposal groups of class i, CTA r walks plain data
                                         // pstart[i][r] .. pstart[i][r+1]-1: whole warp rounds, dealt by cost in thirds of a round
     int pchunk;                         // largest plain slice of any CTA (union over the classes; stride of the staged copy)
+    int ncls;                           // classes the partition was made for: group g of a batch is of class g * ncls / (max_batch / MH_BU)
     CnvWork cw;                         // CNV-affected SSMs: sorted, CTA-major sparse work list (K0c)
     int n_classes;                      // > 0: plain data enter through their per-(node, class, sample) totals (K0d)
     const unsigned long long *cl_sums;  // [K][n_classes][T][2] = {sum a, sum d-a}
@@ -410,7 +411,7 @@ __host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return 
 __host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
 {
     size_t KT = (size_t)K * T;
-    const size_t red = (size_t)maxb > MH_BU * MH_GWARPS ? (size_t)maxb : MH_BU * MH_GWARPS;
+    const size_t red = (size_t)maxb > MH_BU * MH_UNITS ? (size_t)maxb : MH_BU * MH_UNITS;
     return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 4 * (size_t)maxb + 2 * (size_t)K * (MH_CWARPS + 1);
 }
 __host__ __device__ inline size_t mh_smem_ints(int K) { return CTL_WORDS + 2 * (size_t)K; }
@@ -875,7 +876,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         S.state0 = q; q += 2 * S.statestride;
         S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = MAXB * KT; S.o_hast = 2 * MAXB * KT; S.o_logr = 2 * MAXB * KT + MAXB * T;
         S.buf0 = q; q += 2 * S.bufstride;
-        S.red = q; q += (MAXB > MH_BU * MH_GWARPS ? MAXB : MH_BU * MH_GWARPS); S.llh = q; q += MAXB;
+        S.red = q; q += (MAXB > MH_BU * MH_UNITS ? MAXB : MH_BU * MH_UNITS); S.llh = q; q += MAXB;
         S.seen = (unsigned long long *)q; q += 4 * MAXB;
         S.pscratch = q; q += 2 * K * (MH_CWARPS + 1);
         S.ctl = (volatile int *)q; S.tin = (int *)q + CTL_WORDS; S.tout = S.tin + K;
@@ -985,14 +986,17 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         // ---------------- likelihood (param_post) of the CTA's slice for every proposal of the batch
         const int bu = b_nb >= MH_BU ? MH_BU : 1;      // thread groups of MH_BU proposals, or one proposal per group
         const int ngroups = b_nb / bu;                  // proposal groups of the batch
-        const int wpg = ngroups <= MH_GWARPS ? MH_GWARPS / ngroups : 1;
-        if (ngroups <= MH_GWARPS) {
-            // small batch: the first MH_GWARPS warps split into the groups, warps [g*wpg, (g+1)*wpg) share group g; roles are
-            // rotated by g so that the warps holding the expensive head of the sorted CNV list land on different SM
-            // sub-partitions (warp id % 4) in different groups
-            if (warp < MH_GWARPS) {
-                const int gq = warp / wpg, role = (warp - gq * wpg + gq) % wpg;
-                if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, wpg, role, gq, 0, lane, rank, cpc); else mh_likelihood<1>(p, S, sl, cur, wpg, role, gq, 0, lane, rank, cpc);
+        const int wpg = ngroups < MH_UNITS ? MH_UNITS / ngroups : 1;
+        if (ngroups < MH_UNITS) {
+            // smaller batches: every group is cut into wpg shares of the data rounds (share r walks rounds r, r+wpg, ...) so that
+            // there are MH_UNITS units of work again, dealt to the warps in turn like the groups of a full batch.  A group's
+            // class (which partition of the plain data it walks) depends on the group alone, so its shares tile the list.
+            const int gfull = max(1, MAXB / MH_BU);
+#pragma unroll 1
+            for (int v = warp; v < MH_UNITS; v += MH_CWARPS) {
+                const int gq = v & (ngroups - 1), role = v / ngroups;
+                if (bu == MH_BU) mh_likelihood<MH_BU>(p, S, sl, cur, wpg, role, gq, (gq * p.ncls) / gfull, lane, rank, cpc);
+                else mh_likelihood<1>(p, S, sl, cur, wpg, role, gq, 0, lane, rank, cpc);
             }
         } else {
             // large batches: several groups per warp, in turn; a warp's i-th group is of class i (at most MH_PCLASSES: 128

@@ -24,7 +24,7 @@ for k in range(4):
 ncta = eng.get_option("n_sms")
 cyc = np.array([eng.get_option("mh_lik_cta_%d" % r) for r in range(ncta)], dtype=float)
 X = np.array([[eng.get_option("mh_plan_%d_%d" % (c, r)) for c in range(4)] for r in range(ncta)], dtype=float)
-X[:, 0] /= 3.0                                      # thirds -> rounds
+X[:, 0] /= max(1, eng.get_option("mh_plan_classes"))   # fractions -> rounds
 use = X.sum(axis=0) > 0
 w, *_ = np.linalg.lstsq(X[:, use], cyc, rcond=None)
 fit = X[:, use] @ w
@@ -33,3 +33,7 @@ print("rounds per CTA (mean): plain %.2f cnv1 %.2f cnv2 %.2f cnv3 %.2f" % tuple(
 names = [n for n, u in zip(("plain", "cnv1", "cnv2", "cnv3"), use) if u]
 print("fitted cycles per round:", dict(zip(names, np.round(w, 0))), " relative to plain=100:", dict(zip(names, np.round(100 * w / w[0], 1))))
 print("residual rms %.0f cycles (%.2f%% of mean)" % (np.sqrt(np.mean((fit - cyc) ** 2)), 100 * np.sqrt(np.mean((fit - cyc) ** 2)) / cyc.mean()))
+if "-v" in sys.argv:
+    for k in sorted(set(map(tuple, X.tolist()))):
+        sel = np.all(X == np.array(k), axis=1)
+        print("rounds (plain, cnv1, cnv2, cnv3) = (%.2f, %d, %d, %d): %3d CTAs, cycles min %.0f mean %.0f max %.0f" % (k + (sel.sum(), cyc[sel].min(), cyc[sel].mean(), cyc[sel].max())))
