@@ -780,29 +780,37 @@ __device__ __forceinline__ void mh_draw_to_slot(const MhParams &p, const MhSmem 
     __syncwarp();
 }
 
-// ---- the producer warp: draws the proposals this CTA owns of the batch two ahead and posts them in the global ring
+// ---- ring jobs.  Job g = "draw this CTA's share of batch g+2 from state copy e into ring slot (g+2) % MH_RING"; a share is the
+// (proposal, sample) pairs t with (t + 37 g) % cpc == rank, enumerated directly (first + i * cpc): walking all nb*T pairs with a
+// modulo each cost the producer warp more than the draws themselves once T > 1 and made it the pace-setter of the chain.
+// Jobs are posted in the mailbox S.ctl[CTL_JOB..] by thread 0 at the top of batch g and must be complete before the CTA arrives
+// at the barrier of batch g+1.
+__device__ __forceinline__ int mh_job_first(int job, int rank, int cpc) { return (rank - (job * 37) % cpc + cpc) % cpc; }
+__device__ __noinline__ void mh_ring_tasks(const MhParams &p, const MhSmem &S, int job, int rank, int cpc, int scratch, int lane)
+{
+    const int T = p.T;
+    const volatile int *jb = S.ctl + CTL_JOB + 3 * (job & 1);
+    const int e = jb[0], it_first = jb[1], nb = jb[2];
+    double *slot = p.ring + (size_t)((job + 2) % MH_RING) * mh_bufstride(p.K, T, p.max_batch);
+#pragma unroll 1
+    for (int task = mh_job_first(job, rank, cpc); task < nb * T; task += cpc) {
+        const int b = task / T, tp = task - b * T;
+        mh_draw_to_slot(p, S, e, slot, b, tp, (uint32_t)(it_first + b), scratch, lane);
+    }
+    __threadfence();                                                             // ring stores ordered before the "done" flag
+    __syncwarp();
+    if (lane == 0) S.ctl[CTL_PROD_DONE] = job;
+}
+
 __device__ __noinline__ void mh_producer(const MhParams &p, const MhSmem &S, int rank, int cpc, int lane)
 {
-    const int T = p.T, K = p.K;
-    const size_t slot_doubles = mh_bufstride(K, T, p.max_batch);
     int job = 1;                                                                // jobs are numbered by global batch, from 1
 #pragma unroll 1
     for (;;) {
         while (S.ctl[CTL_GEN] < job && !S.ctl[CTL_DONE]) __nanosleep(256);    // idle most of the time: stay out of the issue slots
         if (S.ctl[CTL_GEN] < job) return;                                        // done and nothing new posted
         __threadfence_block();
-        const volatile int *jb = S.ctl + CTL_JOB + 3 * (job & 1);
-        const int e = jb[0], it_first = jb[1], nb = jb[2];
-        double *slot = p.ring + (size_t)((job + 2) % MH_RING) * slot_doubles;
-#pragma unroll 1
-        for (int task = 0; task < nb * T; task++) {
-            if ((task + job * 37) % cpc != rank) continue;                       // one owner CTA per (proposal, sample)
-            const int b = task / T, tp = task - b * T;
-            mh_draw_to_slot(p, S, e, slot, b, tp, (uint32_t)(it_first + b), MH_CWARPS, lane);
-        }
-        __threadfence();                                                         // ring stores ordered before the "done" flag
-        __syncwarp();
-        if (lane == 0) S.ctl[CTL_PROD_DONE] = job;
+        mh_ring_tasks(p, S, job, rank, cpc, MH_CWARPS, lane);
         job++;
     }
 }
