@@ -454,6 +454,8 @@ def main():
                 "cnv_ssm_by_merged_states": stats[:3], "cnv_entry_states": stats[3],
                 "hbm": {"achieved": by_it * its_kernel / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": by_it * its_kernel / 1e9 / hbm_peak,
                         "algorithmic_bytes_per_iteration": by_it,
+                        "note": "what streaming every record from HBM once per iteration would need; the kernel reads them once per "
+                                "LAUNCH and keeps them in shared memory (see traffic), which is why HBM is not the bound",
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}}
 
     cpu_baseline = None
