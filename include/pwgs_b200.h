@@ -173,6 +173,14 @@ int pwgs_math_selftest(int device, int n, const double *x, double *out);
  * denominator for the MH kernel, which is FP64-pipe-bound, not HBM-bound. */
 int pwgs_fp64_peak(int device, double *dfma_per_s);
 
+/* Diagnostics, host code only (no device needed): the MH kernel's work partition for a chain of `cpc` CTAs.  M CNV-affected SSMs
+ * sorted by merged states (n_states = how many have 3, 2, 1), Dp plain data, ncls proposal-group classes (1..3), w = relative cost of
+ * a warp round {plain, cnv1, cnv2, cnv3}.  Out: round_slot [ceil(M/32)] first slot of each CNV round in the CTA-major list,
+ * cta_nc [cpc] CNV-affected SSMs per CTA, pstart [3][cpc+1] plain range boundaries per class, the two slice strides.  Used by the
+ * CPU test-suite to check that every datum is walked exactly once per proposal whatever the shape. */
+int pwgs_plan_partition(int cpc, int M, const int32_t *n_states, int Dp, int ncls, const int32_t *w,
+                        int32_t *round_slot, int32_t *cta_nc, int32_t *pstart, int32_t *cchunk, int32_t *pchunk);
+
 #ifdef __cplusplus
 }
 #endif

@@ -832,6 +832,21 @@ int pwgs_math_selftest(int device, int n, const double *x, double *out)
     return PWGS_OK;
 }
 
+int pwgs_plan_partition(int cpc, int M, const int32_t *n_states, int Dp, int ncls, const int32_t *w,
+                        int32_t *round_slot, int32_t *cta_nc, int32_t *pstart, int32_t *cchunk, int32_t *pchunk)
+{
+    if (cpc < 1 || M < 0 || Dp < 0 || ncls < 1 || ncls > MH_PCLASSES || !n_states || !w || !round_slot || !cta_nc || !pstart || !cchunk || !pchunk)
+        return fail(PWGS_EINVAL, "pwgs_plan_partition: bad argument");
+    if (n_states[0] + n_states[1] + n_states[2] != M) return fail(PWGS_EINVAL, "n_states must add up to M");
+    const int ns[3] = {n_states[0], n_states[1], n_states[2]}, ww[4] = {w[0], w[1], w[2], w[3]};
+    const Partition P = plan_partition(cpc, M, ns, Dp, ww, ncls);
+    for (int u = 0; u < (M + 31) / 32; u++) round_slot[u] = P.round_slot[u];
+    for (int i = 0; i < cpc; i++) cta_nc[i] = P.cta_nc[i];
+    for (size_t i = 0; i < P.pstart.size(); i++) pstart[i] = P.pstart[i];
+    *cchunk = P.cchunk; *pchunk = P.pchunk;
+    return PWGS_OK;
+}
+
 int pwgs_fp64_peak(int device, double *dfma_per_s)
 {
     if (!dfma_per_s) return fail(PWGS_EINVAL, "NULL argument");

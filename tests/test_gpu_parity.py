@@ -134,6 +134,26 @@ def test_mh_collapsed_plain_data_walks_the_same_chain(oracle, gpu_lib, ctas):
     assert rel(got["llh"], want["llh"]) < RTOL
 
 
+@pytest.mark.parametrize("batch", [8, 64, 128])
+@pytest.mark.parametrize("ctas", [0, 40])
+def test_mh_trajectory_many_rounds_per_cta(oracle, gpu_lib, batch, ctas):
+    """Enough data that every CTA holds several warp rounds of both lists, so the cost-levelled partition is exercised with its
+    fractional plain rounds (one, two and three proposal-group classes for batch caps 8 / 64 / 128) and ragged tails
+    (neither list is a multiple of 32).  The chain must still be the oracle's chain."""
+    data, tree = cases.synthetic_case(oracle, n_ssm=20011, n_cnv=60, T=2, K=9, seed=41)
+    iters, std, seed, stream = 150, 30000.0, 99, 3
+    want = oracle.mh_loop(data, tree, iters, std, oracle.RNG_PHILOX, seed, stream)
+    with cases.engine_for(gpu_lib, data, tree) as eng:
+        eng.set_option("mh_batch", batch)
+        eng.set_option("mh_ctas", ctas)
+        got = eng.mh_run(iters, std, seed, stream)
+    assert got["ratio"] * iters == pytest.approx(want["accepted"], abs=1e-9)
+    assert 0 < want["accepted"] < iters
+    assert rel(got["pi"], want["pi"]) < 1e-9
+    assert rel(got["phi"], want["phi"]) < 1e-9
+    assert rel(got["llh"], want["llh"]) < RTOL
+
+
 @pytest.mark.parametrize("K,T,iters,std", [(40, 1, 200, 2000.0), (35, 3, 120, 3000.0), (7, 2, 1, 1000.0), (2, 1, 150, 50.0)])
 def test_mh_trajectory_wide_trees_and_edge_sizes(oracle, gpu_lib, K, T, iters, std):
     """More nodes than lanes in a warp (the proposal warp strides over nodes), several samples, a single iteration, a
