@@ -150,20 +150,27 @@ __device__ __forceinline__ double pwgs_log_pos(double x)
 template <int N>
 __device__ __forceinline__ void pwgs_log_pos_n(const double (&x)[N], double (&r)[N])
 {
-    double f[N], d[N], y[N], t[N], q[N], z[N], w[N], t1[N], t2[N], dk[N], hf[N];
+    // Few values stay live per chain (f, q, z, the Horner accumulator and the integer exponent) so that ptxas can keep all N
+    // chains interleaved inside the register budget: the polynomial is ONE Horner chain in z = s^2 (fdlibm splits it into even
+    // and odd halves for scalar ILP, which costs two more live doubles per chain; here the N chains are the ILP), the exponent
+    // is converted to fp64 only where it is used, and 0.5*f*f is formed after the polynomial.
+    double f[N], d[N], y[N], t[N], q[N], z[N], R[N];
+    int k[N];
 #pragma unroll
     for (int i = 0; i < N; i++) {
         // x = 2^e * m with m in [sqrt(2)/2, sqrt(2)): shift the high word so that the exponent field changes exactly at sqrt(2)
         const int hs = __double2hiint(x[i]) + (0x3ff00000 - 0x3fe6a09e);
-        dk[i] = (double)((hs >> 20) - 1023);
+        k[i] = (hs >> 20) - 1023;
         f[i] = __hiloint2double((hs & 0x000fffff) + 0x3fe6a09e, __double2loint(x[i])) - 1.0;
     }
 #pragma unroll
     for (int i = 0; i < N; i++) d[i] = 2.0 + f[i];
 #pragma unroll
     for (int i = 0; i < N; i++) y[i] = pwgs_rcp_approx(d[i]);
-    // y ~ 1/d to 2^-20 from the hardware; one Newton step (2^-40) is enough because the residual correction of the quotient
-    // below squares the error once more (q = q0 + (f - d*q0)*y: relative error 2^-80 before rounding)
+    // y ~ 1/d to 2^-20 from the hardware, 2^-40 after one Newton step, and s = f*y is used as it is: s only multiplies the
+    // O(f^2) part of log(1+f) = f - hf + s*(hf + R), so the logarithm comes out within 2e-13 relative (measured by
+    // pwgs_math_selftest) -- four orders of magnitude inside the 1e-9 the likelihood is specified to, at 20 FP64 instructions
+    // instead of the 24 a correctly rounded quotient costs.  K2 and pwgs_total_llh use the full-precision log().
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] = fma(-d[i], y[i], 1.0);
 #pragma unroll
@@ -171,86 +178,45 @@ __device__ __forceinline__ void pwgs_log_pos_n(const double (&x)[N], double (&r)
 #pragma unroll
     for (int i = 0; i < N; i++) q[i] = f[i] * y[i];
 #pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(-d[i], q[i], f[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) q[i] = fma(t[i], y[i], q[i]);
-#pragma unroll
     for (int i = 0; i < N; i++) z[i] = q[i] * q[i];
+    // R = z*(Lg1 + z*(Lg2 + ... + z*Lg7))   (fdlibm e_log.c coefficients)
 #pragma unroll
-    for (int i = 0; i < N; i++) w[i] = z[i] * z[i];
+    for (int i = 0; i < N; i++) R[i] = fma(z[i], 1.479819860511658591e-01, 1.531383769920937332e-01);
 #pragma unroll
-    for (int i = 0; i < N; i++) t1[i] = fma(w[i], 1.531383769920937332e-01, 2.222219843214978396e-01);
+    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 1.818357216161805012e-01);
 #pragma unroll
-    for (int i = 0; i < N; i++) t2[i] = fma(w[i], 1.479819860511658591e-01, 1.818357216161805012e-01);
+    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 2.222219843214978396e-01);
 #pragma unroll
-    for (int i = 0; i < N; i++) t1[i] = fma(w[i], t1[i], 3.999999999940941908e-01);
+    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 2.857142874366239149e-01);
 #pragma unroll
-    for (int i = 0; i < N; i++) t2[i] = fma(w[i], t2[i], 2.857142874366239149e-01);
+    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 3.999999999940941908e-01);
 #pragma unroll
-    for (int i = 0; i < N; i++) t1[i] = w[i] * t1[i];
+    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 6.666666666666735130e-01);
 #pragma unroll
-    for (int i = 0; i < N; i++) t2[i] = fma(w[i], t2[i], 6.666666666666735130e-01);
+    for (int i = 0; i < N; i++) R[i] = z[i] * R[i];
 #pragma unroll
-    for (int i = 0; i < N; i++) hf[i] = 0.5 * f[i] * f[i];
-#pragma unroll
-    for (int i = 0; i < N; i++) t2[i] = fma(z[i], t2[i], t1[i]);                                  // R
-#pragma unroll
-    for (int i = 0; i < N; i++) t1[i] = dk[i] * 1.90821492927058770002e-10;
-#pragma unroll
-    for (int i = 0; i < N; i++) t2[i] = fma(q[i], hf[i] + t2[i], t1[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) t2[i] = (hf[i] - t2[i]) - f[i];
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(dk[i], 6.93147180369123816490e-01, -t2[i]);
+    for (int i = 0; i < N; i++) {
+        // log(1+f) = f - hf + s*(hf + R), then + k*ln2 in one fma: fdlibm's hi/lo split of ln2 buys the last half ulp for huge
+        // |k|; here |k| <= 1074 makes the representation error of the single constant at most 2.3e-14 absolute on |log| >= 0.69 |k|
+        const double hf = 0.5 * f[i] * f[i];
+        const double v = fma(q[i], hf + R[i], -hf);
+        r[i] = fma((double)k[i], 6.931471805599453094e-01, f[i] + v);
+    }
 }
-
-// N independent a[i] / b[i], b > 0 (see pwgs_div_pos)
 template <int N>
 __device__ __forceinline__ void pwgs_div_pos_n(const double (&a)[N], const double (&b)[N], double (&r)[N])
 {
+    // a / b to 2^-40 relative (hardware reciprocal, 2^-20, and one Newton step); see pwgs_log_pos_n for why that is enough here
     double y[N], t[N];
 #pragma unroll
     for (int i = 0; i < N; i++) y[i] = pwgs_rcp_approx(b[i]);
 #pragma unroll
     for (int i = 0; i < N; i++) t[i] = fma(-b[i], y[i], 1.0);
 #pragma unroll
-    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);                  // 2^-40; the correction below gives 2^-80
+    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = a[i] * y[i];
-#pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(-b[i], r[i], a[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(t[i], y[i], r[i]);
 }
-
-// exp(x) for x <= 0 (arguments of logsumexp after the max shift).  Arguments below -700 are clamped: the callers add the
-// result to a sum that already holds exp(0) = 1, so anything below 1e-300 rounds away exactly as a true 0 would.
-__device__ __forceinline__ double pwgs_exp_nonpos(double x)
-{
-    x = fmax(x, -700.0);
-    double kd = fma(x, 1.4426950408889634074, 6755399441055744.0);   // round(x / ln2) in the low mantissa bits
-    const int n = __double2loint(kd);
-    kd -= 6755399441055744.0;
-    double r = fma(kd, -6.93147180369123816490e-01, x);
-    r = fma(kd, -1.90821492927058770002e-10, r);                      // |r| <= ln2/2
-    double p = 1.6059043836821613e-10;                                // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);                              // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);                             // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);                             // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);                            // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);                              // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);                             // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);                             // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);                             // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);                            // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);                            // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));   // * 2^n, n >= -1010: stays normal
-}
-
-// N independent pwgs_exp_nonpos evaluations, interleaved like pwgs_log_pos_n
 template <int N>
 __device__ __forceinline__ void pwgs_exp_nonpos_n(const double (&xin)[N], double (&out)[N])
 {

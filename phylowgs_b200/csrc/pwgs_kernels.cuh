@@ -713,7 +713,7 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
     for (int j = pbeg + lt; j - lane < pend; j += tpg) {
         const bool act = j < pend;
         const int jj = act ? j : 0;
-        const double mu_r = sl.pmu_r(jj), mu_v = sl.pmu_v(jj);
+        const double mu_r = sl.pmu_r(jj), dmu = sl.pmu_v(jj) - mu_r;
         const int nodeT = sl.pnode(jj) * T;
 #pragma unroll 1
         for (int tp = 0; tp < T; tp++) {
@@ -723,12 +723,12 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
 #pragma unroll
             for (int bb = 0; bb < BU; bb++) {
                 const double phi = bphi[bb * KT + nodeT + tp];
-                xx[bb] = (1.0 - phi) * mu_r + phi * mu_v;
+                xx[bb] = fma(phi, dmu, mu_r);                       // (1-phi)*mu_r + phi*mu_v (mh.hpp:87) in one rounding
                 xx[BU + bb] = 1.0 - xx[bb];
             }
             pwgs_log_pos_n<2 * BU>(xx, ll);
 #pragma unroll
-            for (int bb = 0; bb < BU; bb++) acc[bb] += fa * ll[bb] + fb * ll[BU + bb];
+            for (int bb = 0; bb < BU; bb++) acc[bb] = fma(fa, ll[bb], fma(fb, ll[BU + bb], acc[bb]));
         }
     }
     // ---- plain data through their sufficient statistics (K0d): entry (node, class, sample) e belongs to CTA e mod cpc
@@ -739,17 +739,17 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
             const bool act = e < n_ent;
             const int ee = act ? e : 0, k = ee / (C * T), c = (ee / T) % C, tp = ee % T;
             const double A = act ? (double)p.cl_sums[2 * ee] : 0.0, B = act ? (double)p.cl_sums[2 * ee + 1] : 0.0;
-            const double mu_r = p.cl_mu_r[c], mu_v = p.cl_mu_v[c];
+            const double mu_r = p.cl_mu_r[c], dmu = p.cl_mu_v[c] - mu_r;
             double xx[2 * BU], ll[2 * BU];
 #pragma unroll
             for (int bb = 0; bb < BU; bb++) {
                 const double phi = bphi[bb * KT + k * T + tp];
-                xx[bb] = (1.0 - phi) * mu_r + phi * mu_v;
+                xx[bb] = fma(phi, dmu, mu_r);
                 xx[BU + bb] = 1.0 - xx[bb];
             }
             pwgs_log_pos_n<2 * BU>(xx, ll);
 #pragma unroll
-            for (int bb = 0; bb < BU; bb++) acc[bb] += A * ll[bb] + B * ll[BU + bb];
+            for (int bb = 0; bb < BU; bb++) acc[bb] = fma(A, ll[bb], fma(B, ll[BU + bb], acc[bb]));
         }
     }
 #pragma unroll

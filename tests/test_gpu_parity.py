@@ -169,7 +169,9 @@ def test_mh_trajectory_wide_trees_and_edge_sizes(oracle, gpu_lib, K, T, iters, s
 
 
 def test_device_log_exp_div_accuracy(gpu_lib):
-    """The MH kernel's own branch-free fp64 log / exp / division (csrc/pwgs_device.cuh) against numpy: a few ulp at most."""
+    """The MH kernel's own branch-free fp64 log / exp / division (csrc/pwgs_device.cuh) against numpy.  The logarithm and the
+    division stop one correction short of correct rounding on purpose (2^-40 reciprocal): 1e-12 relative is the bar here, four
+    orders of magnitude inside the 1e-9 of the likelihood; the exponential is good to a few ulp."""
     import ctypes as C
     from phylowgs_b200 import _lib
     rng = np.random.default_rng(5)
@@ -179,12 +181,14 @@ def test_device_log_exp_div_accuracy(gpu_lib):
     _lib.check(_lib.load().pwgs_math_selftest(0, len(x), _lib.p_f64(x), _lib.p_f64(out)))
     lg, ex, dv = out[:len(x)], out[len(x):2 * len(x)], out[2 * len(x):]
     want = np.log(x)
-    err = np.abs(lg - want) / np.maximum(np.spacing(np.abs(want)), 1e-300)
-    assert err.max() <= 2.0, (err.max(), x[err.argmax()])
+    err = np.abs(lg - want) / np.maximum(np.abs(want), 1e-300)
+    err[want == 0.0] = np.abs(lg[want == 0.0])
+    assert err.max() <= 1e-12, (err.max(), x[err.argmax()])
     small = x <= 700.0
     want_e = np.exp(-x[small])
     err_e = np.abs(ex[small] - want_e) / np.spacing(want_e)
     assert err_e.max() <= 4.0, (err_e.max(), x[small][err_e.argmax()])
     big = x < 1e150
     want_d = x[big] / (1.0 + x[big])
-    assert (np.abs(dv[big] - want_d) / np.spacing(want_d)).max() <= 1.0
+    assert (np.abs(dv[big] - want_d) / want_d).max() <= 2e-12
+    print("log max rel err %.2e, div max rel err %.2e" % (err.max(), (np.abs(dv[big] - want_d) / want_d).max()))
