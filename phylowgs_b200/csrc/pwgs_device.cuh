@@ -153,7 +153,7 @@ __device__ __forceinline__ void pwgs_log_pos_n(const double (&x)[N], double (&r)
     // Few values stay live per chain (f, q, z, the Horner accumulator and the integer exponent) so that ptxas can keep all N
     // chains interleaved inside the register budget: the polynomial is ONE Horner chain in z = s^2 (fdlibm splits it into even
     // and odd halves for scalar ILP, which costs two more live doubles per chain; here the N chains are the ILP), the exponent
-    // is converted to fp64 only where it is used, and 0.5*f*f is formed after the polynomial.
+    // is converted to fp64 only where it is used, and the tail needs nothing but f, s and the polynomial.
     double f[N], d[N], y[N], t[N], q[N], z[N], R[N];
     int k[N];
 #pragma unroll
@@ -196,11 +196,11 @@ __device__ __forceinline__ void pwgs_log_pos_n(const double (&x)[N], double (&r)
     for (int i = 0; i < N; i++) R[i] = z[i] * R[i];
 #pragma unroll
     for (int i = 0; i < N; i++) {
-        // log(1+f) = f - hf + s*(hf + R), then + k*ln2 in one fma: fdlibm's hi/lo split of ln2 buys the last half ulp for huge
-        // |k|; here |k| <= 1074 makes the representation error of the single constant at most 2.3e-14 absolute on |log| >= 0.69 |k|
-        const double hf = 0.5 * f[i] * f[i];
-        const double v = fma(q[i], hf + R[i], -hf);
-        r[i] = fma((double)k[i], 6.931471805599453094e-01, f[i] + v);
+        // log(1+f) = 2s + s*R and 2s = f - s*f  =>  log(1+f) = f - s*(f - R) (fdlibm's form for small exponents; its 0.5 f^2
+        // variant only buys the last ulp), then + k*ln2 in one fma: the hi/lo split of ln2 matters for huge |k| only; here
+        // |k| <= 1074 makes the representation error of the single constant at most 2.3e-14 absolute on |log| >= 0.69 |k|
+        const double u = fma(-q[i], f[i] - R[i], f[i]);
+        r[i] = fma((double)k[i], 6.931471805599453094e-01, u);
     }
 }
 template <int N>
