@@ -405,7 +405,8 @@ struct MhSmem {
     volatile int *ctl;                              // producer mailbox, see MhCtl
     int *tin, *tout;                                // [K]
 };
-enum MhCtl { CTL_GEN = 0, CTL_DONE = 1, CTL_PROD_DONE = 2, CTL_ABORT = 3, CTL_JOB = 4 /* 2 x {state, it, nb} */, CTL_PRANGE = 12 /* MH_PCLASSES x {first, count} */, CTL_WORDS = 20 };
+enum MhCtl { CTL_GEN = 0, CTL_DONE = 1, CTL_PROD_DONE = 2, CTL_ABORT = 3, CTL_JOB = 4 /* 2 x {state, it, nb} */, CTL_PRANGE = 12 /* MH_PCLASSES x {first, count} */,
+             CTL_OK = 20 /* PWGS_MAX_BATCH / 32 ballots of the accept test */, CTL_WORDS = 20 + PWGS_MAX_BATCH / 32 };
 
 __host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return 2 * (size_t)maxb * K * T + (size_t)maxb * T + maxb; }
 __host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
@@ -1076,12 +1077,25 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
             if (tid < n1_nb * T) f_h = __ldcg(slot + S.o_hast + tid);
             if (tid < n1_nb) f_r = __ldcg(slot + S.o_logr + tid);
         }
-        if (tid < MAXB) {                              // the batch's totals = what was added to this parity since we last looked
-            const ulonglong2 now = __ldcg((const ulonglong2 *)(p.sums + ((size_t)parity * PWGS_MAX_BATCH + tid) * MH_SUM_STRIDE));
-            unsigned long long *sn = S.seen + (size_t)parity * 2 * MAXB + 2 * tid;
-            const unsigned long long was_x = sn[0], was_y = sn[1];
-            sn[0] = now.x; sn[1] = now.y;
-            S.llh[tid] = (double)(long long)(now.x - was_x) + (double)(long long)(now.y - was_y) * 2.220446049250313e-16;
+        if (warp < PWGS_MAX_BATCH / 32) {
+            // thread b: the batch's total for proposal b = what was added to this parity since we last looked, and right away
+            // the accept test of proposal b (mh.cpp:73-100); one ballot per warp, combined after the sync below
+            bool ok = false;
+            if (tid < MAXB) {
+                const ulonglong2 now = __ldcg((const ulonglong2 *)(p.sums + ((size_t)parity * PWGS_MAX_BATCH + tid) * MH_SUM_STRIDE));
+                unsigned long long *sn = S.seen + (size_t)parity * 2 * MAXB + 2 * tid;
+                const unsigned long long was_x = sn[0], was_y = sn[1];
+                sn[0] = now.x; sn[1] = now.y;
+                const double val = (double)(long long)(now.x - was_x) + (double)(long long)(now.y - was_y) * 2.220446049250313e-16;
+                S.llh[tid] = val;
+                if (j >= 0 && tid < b_nb) {
+                    double a = val - cur_llh;
+                    for (int tp = 0; tp < T; tp++) a += S.hast(cur)[tid * T + tp];
+                    ok = S.logr(cur)[tid] < a;
+                }
+            }
+            const unsigned m = __ballot_sync(PWGS_FULL_MASK, ok);
+            if (lane == 0) S.ctl[CTL_OK + warp] = (int)m;
         }
         if (fetch) {
             double *dst = S.prop_pi(cur ^ 1);
@@ -1094,21 +1108,14 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         consumer_sync();
         MH_PROF(4);
 
-        // ---------------- accept / reject (mh.cpp:73-100): lane b tests proposal b, the first accepted one wins
+        // ---------------- accept / reject: the tests were made while the totals were read; pick the first accepted proposal
         int sel = -1;
         if (j < 0) {
             cur_llh = S.llh[0];
         } else {
-            for (int base = 0; base < b_nb && sel < 0; base += 32) {
-                const int b = base + lane;
-                bool ok = false;
-                if (b < b_nb) {
-                    double a = S.llh[b] - cur_llh;
-                    for (int tp = 0; tp < T; tp++) a += S.hast(cur)[b * T + tp];
-                    ok = S.logr(cur)[b] < a;
-                }
-                const unsigned m = __ballot_sync(PWGS_FULL_MASK, ok);
-                if (m) sel = base + __ffs(m) - 1;
+            for (int w = 0; w < PWGS_MAX_BATCH / 32 && sel < 0; w++) {          // the first accepted proposal wins
+                const unsigned m = (unsigned)S.ctl[CTL_OK + w];
+                if (m) sel = 32 * w + __ffs(m) - 1;
             }
         }
         pc[7]++;
