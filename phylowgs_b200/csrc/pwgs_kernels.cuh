@@ -1020,20 +1020,21 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
 
         // ---------------- publish the CTA's partial sums and arrive at the chain barrier (release)
         const int parity = g & 1;
-        if (warp == 0) {
+        if (warp < PWGS_MAX_BATCH / 32) {
             // The CTA's partial sum t goes into the chain's running totals as two integers, rint(t) and the remainder in
             // units of 2^-52: integer adds commute, so every CTA later reads the same bits whatever order the adds landed in,
             // and the total is exact (no rounding between CTAs).  The totals are never reset: readers take differences.
+            // Thread b publishes proposal b; the four warps meet in their own barrier before thread 0 arrives (release).
             unsigned long long *acc = p.sums + (size_t)parity * MH_SUM_STRIDE * PWGS_MAX_BATCH;
-            for (int b = lane; b < b_nb; b += 32) {
+            if (tid < b_nb) {
                 double t = 0.0;
-                for (int r = 0; r < wpg; r++) t += S.red[b * wpg + r];
+                for (int r = 0; r < wpg; r++) t += S.red[tid * wpg + r];
                 const double th = rint(t);
-                atomicAdd(acc + MH_SUM_STRIDE * b, (unsigned long long)(long long)th);
-                atomicAdd(acc + MH_SUM_STRIDE * b + 1, (unsigned long long)__double2ll_rn((t - th) * 4503599627370496.0));
+                atomicAdd(acc + MH_SUM_STRIDE * tid, (unsigned long long)(long long)th);
+                atomicAdd(acc + MH_SUM_STRIDE * tid + 1, (unsigned long long)__double2ll_rn((t - th) * 4503599627370496.0));
             }
-            __syncwarp();
-            if (lane == 0) {
+            asm volatile("bar.sync 2, %0;" ::"n"(PWGS_MAX_BATCH) : "memory");
+            if (tid == 0) {
                 if (dist) {                                                      // our share of batch g+1 must be in the ring
                     const long long t0 = clock64();
                     unsigned spins = 0;
