@@ -48,7 +48,7 @@ FP64_LOG = 16                     # pwgs_log_pos_n: 2 DADD, reciprocal 2, quotie
 FP64_PLAIN_TERM = 2 + 2 * FP64_LOG + 2                     # mu (one fma), 1-mu ; two logs ; two fmas into the sum           = 36
 FP64_CNV_STATE = 10 + 2 * FP64_LOG                         # nr+nv, mixture mean (division = 3), select, two logs, combine = 42
 FP64_CNV_PER_ENTRY = 2                                     # two DFMAs per sparse (node, state) entry
-FP64_LSE_EXTRA_STATE = 43                                  # running logsumexp: max, two exps (19 each), fma
+FP64_LSE_EXTRA_STATE = 24                                  # running logsumexp: difference, ONE exp (19), selects, fma
 FP64_LSE_FINAL = FP64_LOG + 1                              # log of the sum (only when an SSM has more than one merged state)
 
 

@@ -114,7 +114,7 @@ int pwgs_get_data_states(pwgs_ctx *ctx, int32_t *M, int32_t *ssm_of_m, int32_t *
  * data enter the MH likelihood through exact integer totals per (node, error-rate class, sample) instead of one term per datum;
  * off by default, available when the data have at most 16 distinct (mu_r, mu_v) pairs).  "mh_w_plain", "mh_w_cnv1", "mh_w_cnv2",
  * "mh_w_cnv3": relative cost of a warp round (32 data) of plain data / of CNV-affected SSMs with 1, 2, 3 merged states, used to
- * deal whole rounds to the chain's CTAs (defaults 100 / 170 / 433 / 696, fitted to measured per-CTA cycles).  Diagnostics with
+ * deal whole rounds to the chain's CTAs (defaults 100 / 183 / 429 / 675, fitted to measured per-CTA cycles).  Diagnostics with
  * "mh_profile" = 1: "mh_prof_0".."mh_prof_7" (CTA 0's cycles per phase), "mh_lik_min/max/sum" and "mh_lik_cta_<r>" (likelihood
  * cycles of the chain's CTAs), "mh_plan_<class>_<r>" (rounds of CTA r: class 0 = plain, in thirds; 1..3 = CNV by states). */
 int pwgs_set_option(pwgs_ctx *ctx, const char *name, int64_t value);

@@ -71,7 +71,7 @@ struct pwgs_ctx {
     int pchunk = 0;
     std::vector<int> plan_counts;                // [cpc][4] rounds per CTA: plain thirds, CNV rounds with 1 / 2 / 3 states (diagnostics)
     const int *pstart_dev = nullptr;
-    int opt_w[4] = {100, 170, 433, 696};             // relative cost of a warp round: plain, CNV-affected with 1 / 2 / 3 merged states
+    int opt_w[4] = {100, 183, 429, 675};             // relative cost of a warp round: plain, CNV-affected with 1 / 2 / 3 merged states
     bool work_valid = false;
     DevBuf<int> code_tmp, enode_tmp, pos, w_a, w_d, w_code, w_enode, overflow, plan;
     DevBuf<int4> ecoef_tmp, w_ecoef;

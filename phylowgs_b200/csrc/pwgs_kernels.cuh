@@ -685,15 +685,17 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
 #pragma unroll
                     for (int bb = 0; bb < BU; bb++) { mx[bb] = val[bb]; sm[bb] = 1.0; }
                 } else {
-                    double nm[BU], x1[BU], x2[BU];
+                    // running logsumexp: of exp(mx - nm) and exp(val - nm) one is exp(0) = 1, so one exponential does
+                    double xe[BU], ee[BU];
 #pragma unroll
-                    for (int bb = 0; bb < BU; bb++) { nm[bb] = fmax(mx[bb], val[bb]); x1[bb] = mx[bb] - nm[bb]; x2[bb] = val[bb] - nm[bb]; }
-                    double xe[2 * BU], ee[2 * BU];
+                    for (int bb = 0; bb < BU; bb++) xe[bb] = -fabs(mx[bb] - val[bb]);
+                    pwgs_exp_nonpos_n<BU>(xe, ee);
 #pragma unroll
-                    for (int bb = 0; bb < BU; bb++) { xe[bb] = x1[bb]; xe[BU + bb] = x2[bb]; }
-                    pwgs_exp_nonpos_n<2 * BU>(xe, ee);
-#pragma unroll
-                    for (int bb = 0; bb < BU; bb++) { sm[bb] = fma(sm[bb], ee[bb], ee[BU + bb]); mx[bb] = nm[bb]; }
+                    for (int bb = 0; bb < BU; bb++) {
+                        const bool up = val[bb] > mx[bb];
+                        sm[bb] = fma(sm[bb], up ? ee[bb] : 1.0, up ? 1.0 : ee[bb]);
+                        mx[bb] = up ? val[bb] : mx[bb];
+                    }
                 }
             }
             if (numax <= 1) {

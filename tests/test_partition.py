@@ -7,7 +7,7 @@ import pytest
 
 from phylowgs_b200 import _lib
 
-W = np.array([100, 160, 400, 640], dtype=np.int32)
+W = np.array([100, 183, 429, 675], dtype=np.int32)
 
 
 def plan(cpc, n_states, Dp, ncls, w=W):
