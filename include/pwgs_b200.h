@@ -109,7 +109,7 @@ int pwgs_get_lbc(pwgs_ctx *ctx, double *out /* [D*T] log_bin_coeff(d,a), mh.cpp:
  * Pass NULL arrays to query M only. */
 int pwgs_get_data_states(pwgs_ctx *ctx, int32_t *M, int32_t *ssm_of_m, int32_t *coef);
 
-/* Tuning knobs: "mh_batch" (largest speculative batch of proposals per grid barrier: a power of two in 1..128 = default; the kernel
+/* Tuning knobs: "mh_batch" (largest speculative batch of proposals per grid barrier: a power of two in 1..256 = default; the kernel
  * adapts the actual batch to the running acceptance rate), "mh_ctas" (CTAs per chain, 0 = all SMs) and "mh_collapse" (1: plain
  * data enter the MH likelihood through exact integer totals per (node, error-rate class, sample) instead of one term per datum;
  * off by default, available when the data have at most 16 distinct (mu_r, mu_v) pairs).  "mh_w_plain", "mh_w_cnv1", "mh_w_cnv2",
@@ -174,9 +174,9 @@ int pwgs_math_selftest(int device, int n, const double *x, double *out);
 int pwgs_fp64_peak(int device, double *dfma_per_s);
 
 /* Diagnostics, host code only (no device needed): the MH kernel's work partition for a chain of `cpc` CTAs.  M CNV-affected SSMs
- * sorted by merged states (n_states = how many have 3, 2, 1), Dp plain data, ncls proposal-group classes (1..3), w = relative cost of
+ * sorted by merged states (n_states = how many have 3, 2, 1), Dp plain data, ncls proposal-group classes (1..6), w = relative cost of
  * a warp round {plain, cnv1, cnv2, cnv3}.  Out: round_slot [ceil(M/32)] first slot of each CNV round in the CTA-major list,
- * cta_nc [cpc] CNV-affected SSMs per CTA, pstart [3][cpc+1] plain range boundaries per class, the two slice strides.  Used by the
+ * cta_nc [cpc] CNV-affected SSMs per CTA, pstart [6][cpc+1] plain range boundaries per class, the two slice strides.  Used by the
  * CPU test-suite to check that every datum is walked exactly once per proposal whatever the shape. */
 int pwgs_plan_partition(int cpc, int M, const int32_t *n_states, int Dp, int ncls, const int32_t *w,
                         int32_t *round_slot, int32_t *cta_nc, int32_t *pstart, int32_t *cchunk, int32_t *pchunk);

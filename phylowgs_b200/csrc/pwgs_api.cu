@@ -445,9 +445,12 @@ static Partition plan_partition(int cpc, int M, const int n_states[3] /* SSMs wi
 // proposal-group classes of a full batch of B proposals: a warp's 1st, 2nd, 3rd group (see the large-batch loop of mh_kernel)
 static int mh_group_classes(int B)
 {
-    // 128 proposals = 32 groups over 11 warps: a warp's 1st / 2nd / 3rd group; smaller caps cut their groups into shares of the
-    // data rounds (MH_UNITS units again) and use two classes of groups; tiny caps have a single group
-    return B >= MH_BU * MH_UNITS ? MH_PCLASSES : (B >= 2 * MH_BU ? 2 : 1);
+    // a full batch gives every warp whole proposal groups in turn, its i-th group being of class i: 256 proposals = 64 groups
+    // over 11 warps = 6 classes, 128 = 3; smaller caps cut their groups into shares of the data rounds (MH_UNITS units again)
+    // and use two classes of groups; tiny caps have a single group
+    const int groups = B / MH_BU;
+    if (groups >= MH_UNITS) return std::min(MH_PCLASSES, (groups + MH_CWARPS - 1) / MH_CWARPS);
+    return B >= 2 * MH_BU ? 2 : 1;
 }
 
 static int prepare_cnv_work(pwgs_ctx *c, int cpc, int collapse, int ncls)
@@ -724,7 +727,7 @@ int pwgs_set_option(pwgs_ctx *c, const char *name, int64_t value)
     if (!c || !name) return fail(PWGS_EINVAL, "NULL argument");
     std::string n(name);
     if (n == "mh_batch") {
-        if (value < 1 || value > PWGS_MAX_BATCH || (value & (value - 1))) return fail(PWGS_EINVAL, "mh_batch must be a power of two in 1..128");
+        if (value < 1 || value > PWGS_MAX_BATCH || (value & (value - 1))) return fail(PWGS_EINVAL, "mh_batch must be a power of two in 1..256");
         c->opt_batch = (int)value;
     } else if (n == "mh_ctas") {
         if (value < 0) return fail(PWGS_EINVAL, "mh_ctas must be >= 0");

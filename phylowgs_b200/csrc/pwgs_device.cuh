@@ -5,7 +5,7 @@
 #include <stdint.h>
 #include <math.h>
 
-#define PWGS_MAX_BATCH 128
+#define PWGS_MAX_BATCH 256
 #define PWGS_FULL_MASK 0xffffffffu
 
 // ------------------------------------------------------------------ tree tables

@@ -345,7 +345,10 @@ __global__ void collapse_kernel(int Dp, int T, int C, const int *__restrict__ pa
 #define MH_RING 4                        // slots of the global proposal ring
 #define MH_WATCHDOG_CYCLES 8000000000ll  // ~4 s of SM clock: a barrier that has not completed by then never will
 #define MH_SUM_STRIDE 16                 // 64-bit words between the running totals of two proposals: one L2 line each
-#define MH_PCLASSES 3                    // proposal-group classes of the plain partition: a warp's 1st / 2nd / 3rd group of a full batch
+#define MH_PCLASSES 6                    // proposal-group classes of the plain partition: a warp's 1st .. 6th group of a full batch
+#define MH_NARROW_BATCH 128              // batch cap while accepts are recent; the full cap (PWGS_MAX_BATCH) opens up after
+#define MH_WIDE_AFTER 8                  // this many all-reject batches in a row: an accept wastes the rest of its batch, so the wide
+                                         // batch (half as many chain barriers per iteration) only pays at very low acceptance
 #define MH_DIST_MIN_CTAS 32              // chains with fewer CTAs draw every proposal locally in every CTA
 
 struct MhParams {
@@ -406,7 +409,7 @@ struct MhSmem {
     int *tin, *tout;                                // [K]
 };
 enum MhCtl { CTL_GEN = 0, CTL_DONE = 1, CTL_PROD_DONE = 2, CTL_ABORT = 3, CTL_JOB = 4 /* 2 x {state, it, nb} */, CTL_PRANGE = 12 /* MH_PCLASSES x {first, count} */,
-             CTL_OK = 20 /* PWGS_MAX_BATCH / 32 ballots of the accept test */, CTL_WORDS = 20 + PWGS_MAX_BATCH / 32 };
+             CTL_OK = 12 + 2 * MH_PCLASSES /* PWGS_MAX_BATCH / 32 ballots of the accept test */, CTL_WORDS = 12 + 2 * MH_PCLASSES + PWGS_MAX_BATCH / 32 };
 
 __host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return 2 * (size_t)maxb * K * T + (size_t)maxb * T + maxb; }
 __host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
@@ -421,6 +424,8 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 __device__ __forceinline__ int pow2_floor(int x) { return x <= 0 ? 0 : 1 << (31 - __clz(x)); }
 // size of the batch that follows a batch of n rejected proposals, with `left` iterations still to do
 __device__ __forceinline__ int next_batch(int n, int left, int maxb) { return pow2_floor(min(min(maxb, 2 * n), left)); }
+// cap of the batch that runs after jn all-reject batches in a row
+__device__ __forceinline__ int batch_cap(int jn, int maxb) { return jn >= MH_WIDE_AFTER ? maxb : min(maxb, MH_NARROW_BATCH); }
 
 // single out-of-line copy of the (large) lgamma routine
 __device__ __noinline__ double pwgs_lgamma(double x) { return lgamma(x); }
@@ -985,8 +990,8 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
     while (b_nb > 0) {
         // the batches that follow if everything is rejected
         const int n1_it = j < 0 ? 0 : b_it + b_nb;
-        const int n1_nb = j < 0 ? pow2_floor(min(1, p.iters)) : next_batch(b_nb, p.iters - n1_it, MAXB);
-        const int n2_it = n1_it + n1_nb, n2_nb = next_batch(n1_nb, p.iters - n2_it, MAXB);
+        const int n1_nb = j < 0 ? pow2_floor(min(1, p.iters)) : next_batch(b_nb, p.iters - n1_it, batch_cap(j + 1, MAXB));
+        const int n2_it = n1_it + n1_nb, n2_nb = next_batch(n1_nb, p.iters - n2_it, batch_cap(j + 2, MAXB));
         if (dist && tid == 0 && g >= 1) {              // post job g: draw batch g+2 from state copy e
             volatile int *jb = S.ctl + CTL_JOB + 3 * (g & 1);
             jb[0] = e; jb[1] = n2_it; jb[2] = n2_nb;
@@ -1139,7 +1144,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         e ^= 1;
         b_it += sel + 1;
         // after an accept at position sel, expect the next one about as far away: batch = pow2 >= sel+1
-        b_nb = pow2_floor(min(min(MAXB, max(1, 2 * pow2_floor(sel + 1))), p.iters - b_it));
+        b_nb = pow2_floor(min(min(batch_cap(0, MAXB), max(1, 2 * pow2_floor(sel + 1))), p.iters - b_it));
         j = 0;
         consumer_sync();
         mh_refresh_state(p, S, e, tid, warp, lane);
@@ -1148,7 +1153,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         if (!dist) {
             mh_draw_local(p, S, e, cur ^ 1, b_nb, b_it, warp, lane);
         } else {
-            const int n1b = next_batch(b_nb, p.iters - (b_it + b_nb), MAXB);
+            const int n1b = next_batch(b_nb, p.iters - (b_it + b_nb), batch_cap(1, MAXB));
             if (mh_epoch_start(p, S, e, cur ^ 1, b_nb, b_it, n1b, rank, cpc, bar_no, tid, warp, lane)) break;
             bar_no++;
             es_ready = n1b > 0;

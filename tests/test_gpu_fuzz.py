@@ -28,7 +28,7 @@ def test_random_shapes_and_options_walk_the_oracle_chain(oracle, gpu_lib):
         iters = int(rng.choice([1, 7, 60, 250]))
         std = float(rng.choice([30.0, 300.0, 3000.0, 30000.0]))
         seed, stream = int(rng.integers(1, 2 ** 40)), int(rng.integers(0, 1000))
-        opts = dict(mh_batch=int(rng.choice([1, 2, 8, 16, 64, 128])), mh_ctas=int(rng.choice([0, 0, 1, 2, 7, 32, 60, 148])),
+        opts = dict(mh_batch=int(rng.choice([1, 2, 8, 16, 64, 128, 256])), mh_ctas=int(rng.choice([0, 0, 1, 2, 7, 32, 60, 148])),
                     mh_stage=int(rng.integers(0, 2)), mh_dist=int(rng.choice([-1, -1, 0, 1])), mh_collapse=int(rng.integers(0, 2)))
         want = oracle.mh_loop(data, tree, iters, std, oracle.RNG_PHILOX, seed, stream)
         with cases.engine_for(gpu_lib, data, tree) as eng:

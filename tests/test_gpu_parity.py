@@ -76,7 +76,7 @@ def test_bundled_golden_cases(oracle, gpu_lib):
             assert rel(eng.total_llh(gpu_lib.SEM_PY), oracle.total_llh(data, tree, oracle.SEM_PY)) < RTOL
 
 
-@pytest.mark.parametrize("batch", [1, 4, 32, 128])
+@pytest.mark.parametrize("batch", [1, 4, 32, 128, 256])
 @pytest.mark.parametrize("ctas", [1, 3, 0])
 @pytest.mark.parametrize("stage", [1, 0])
 @pytest.mark.parametrize("dist", [-1, 1])
@@ -134,7 +134,7 @@ def test_mh_collapsed_plain_data_walks_the_same_chain(oracle, gpu_lib, ctas):
     assert rel(got["llh"], want["llh"]) < RTOL
 
 
-@pytest.mark.parametrize("batch", [8, 64, 128])
+@pytest.mark.parametrize("batch", [8, 64, 128, 256])
 @pytest.mark.parametrize("ctas", [0, 40])
 def test_mh_trajectory_many_rounds_per_cta(oracle, gpu_lib, batch, ctas):
     """Enough data that every CTA holds several warp rounds of both lists, so the cost-levelled partition is exercised with its

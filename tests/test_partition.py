@@ -8,6 +8,7 @@ import pytest
 from phylowgs_b200 import _lib
 
 W = np.array([100, 183, 429, 675], dtype=np.int32)
+NCLS_MAX = 6                                    # MH_PCLASSES: a warp's 1st .. 6th proposal group of a 256-proposal batch
 
 
 def plan(cpc, n_states, Dp, ncls, w=W):
@@ -16,7 +17,7 @@ def plan(cpc, n_states, Dp, ncls, w=W):
     ns = np.array(n_states, dtype=np.int32)
     round_slot = np.full(max((M + 31) // 32, 1), -1, dtype=np.int32)
     cta_nc = np.zeros(cpc, dtype=np.int32)
-    pstart = np.zeros((3, cpc + 1), dtype=np.int32)
+    pstart = np.zeros((NCLS_MAX, cpc + 1), dtype=np.int32)
     cc, pc = C.c_int32(0), C.c_int32(0)
     p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))      # noqa: E731
     _lib.check(L.pwgs_plan_partition(cpc, M, p(ns), Dp, ncls, p(np.ascontiguousarray(w)), p(round_slot), p(cta_nc), p(pstart),
@@ -29,7 +30,7 @@ SHAPES = [(148, (0, 5732, 9183), 35385), (148, (0, 0, 0), 20000), (148, (7, 0, 0
 
 
 @pytest.mark.parametrize("cpc,n_states,Dp", SHAPES)
-@pytest.mark.parametrize("ncls", [1, 2, 3])
+@pytest.mark.parametrize("ncls", [1, 2, 3, 6])
 def test_partition_covers_everything_once(cpc, n_states, Dp, ncls):
     M = sum(n_states)
     round_slot, cta_nc, pstart, cchunk, pchunk = plan(cpc, n_states, Dp, ncls)
@@ -47,7 +48,7 @@ def test_partition_covers_everything_once(cpc, n_states, Dp, ncls):
             r_of = np.nonzero(cta == c)[0]
             assert (np.diff(local[r_of]) > 0).all()
     # plain list: per class, the CTAs' ranges tile [0, Dp) in whole rounds; unused classes repeat class 0
-    for i in range(3):
+    for i in range(NCLS_MAX):
         b = pstart[i]
         assert b[0] == 0 and b[-1] == Dp and (np.diff(b) >= 0).all()
         assert all(x % 32 == 0 or x == Dp for x in b)
@@ -62,14 +63,18 @@ def test_partition_levels_the_cost():
     """config 3's shape: loads (in weight units) within one third of a plain round of each other, but for CTAs that hold nothing
     but expensive rounds."""
     cpc, n_states, Dp = 148, (0, 5732, 9183), 35385
-    round_slot, cta_nc, pstart, cchunk, pchunk = plan(cpc, n_states, Dp, 3)
+    round_slot, cta_nc, pstart, cchunk, pchunk = plan(cpc, n_states, Dp, 1)
     M = sum(n_states)
     load = np.zeros(cpc)
     for u in range((M + 31) // 32):
         r = 32 * u
         cls = 3 if r < n_states[0] else (2 if r < n_states[0] + n_states[1] else 1)
         load[round_slot[u] // cchunk] += W[cls]
-    thirds = sum(np.ceil(np.diff(pstart[i]) / 32.0) for i in range(3))
-    load += thirds * W[0] / 3.0
-    assert load.max() - load.min() <= W[0] / 3.0 + 1e-9
+    for ncls in (3, 6):
+        round_slot, cta_nc, pstart, cchunk, pchunk = plan(cpc, n_states, Dp, ncls)
+        frac = sum(np.ceil(np.diff(pstart[i]) / 32.0) for i in range(ncls))
+        total = load + frac * W[0] / ncls
+        assert total.max() - total.min() <= W[0] / ncls + 1e-9
+        assert total.max() / total.mean() < 1.02
+    return
     assert load.max() / load.mean() < 1.02
