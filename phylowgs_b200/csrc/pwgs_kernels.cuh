@@ -340,6 +340,7 @@ __global__ void collapse_kernel(int Dp, int T, int C, const int *__restrict__ pa
                                          // SM sub-partition, the most that fit at 168 registers (8 interleaved chains of fp64 logarithms per thread)
 #define MH_UNITS 32                      // work units (proposal group x share of the data rounds) a batch is cut into: ~3 per consumer warp
 #define MH_CONSUMERS (MH_CWARPS * 32)
+static_assert(PWGS_MAX_BATCH / 32 <= MH_CWARPS, "the publish / read-totals steps use one consumer thread per proposal");
 #define MH_THREADS (MH_CONSUMERS + 32)   // + one producer warp (proposal draws for the ring)
 #define MH_BU 4                          // proposals evaluated per thread in one pass over its data
 #define MH_RING 4                        // slots of the global proposal ring
