@@ -41,7 +41,9 @@ enum {
 /* Likelihood conventions. */
 enum {
     PWGS_SEM_MH = 0,    /* C++: mh.hpp:80-163 — 4 states, 1/4 weights, states substituted as params.py:160-166 */
-    PWGS_SEM_PY = 1     /* Python: data.py:47-126 — states with nv==0 dropped, rest weighted 1/len */
+    PWGS_SEM_PY = 1,    /* Python: data.py:47-126 — states with nv==0 dropped, rest weighted 1/len */
+    PWGS_LAYOUT_COLS = 0x100  /* OR-ed into `semantics` of pwgs_llh_rows / pwgs_llh_block: out[k*n_rows + r] (one contiguous column per
+                                 node, what the assignment sweep reads) instead of out[r*n_cols + k] */
 };
 
 const char *pwgs_last_error(void);

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpwgs_b200.so")
 
 SEM_MH, SEM_PY = 0, 1
+LAYOUT_COLS = 0x100                      # PWGS_LAYOUT_COLS: column-major output of pwgs_llh_rows / pwgs_llh_block
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)

@@ -635,6 +635,8 @@ int pwgs_llh_block(pwgs_ctx *c, int n_rows, const int32_t *rows, int n_cols, con
     if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
     if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called first");
     if (n_rows < 0 || (n_rows > 0 && (!rows || !out))) return fail(PWGS_EINVAL, "rows/out NULL");
+    const int col_major = (semantics & PWGS_LAYOUT_COLS) ? 1 : 0;
+    semantics &= ~PWGS_LAYOUT_COLS;
     if (semantics != PWGS_SEM_MH && semantics != PWGS_SEM_PY) return fail(PWGS_EINVAL, "unknown semantics");
     if (cols == nullptr) n_cols = c->K;
     if (n_cols < 0) return fail(PWGS_EINVAL, "n_cols must be >= 0");
@@ -647,7 +649,7 @@ int pwgs_llh_block(pwgs_ctx *c, int n_rows, const int32_t *rows, int n_cols, con
     if (cols) CUDA_TRY(c->cols.upload(cols, n_cols, c->stream));
     CUDA_TRY(c->scratch.alloc(total));
     pair_llh_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(data_view(c), tree_view(c), 0, n_rows, c->rows.p, n_cols,
-                                                                            cols ? c->cols.p : nullptr, semantics, kLogTinyMh, kLogTinyPy,
+                                                                            cols ? c->cols.p : nullptr, col_major, semantics, kLogTinyMh, kLogTinyPy,
                                                                             kLogQuarter, c->scratch.p);
     CUDA_TRY(cudaGetLastError());
     c->n_launches++;
@@ -672,7 +674,7 @@ int pwgs_total_llh(pwgs_ctx *c, int semantics, double *out)
     if (semantics != PWGS_SEM_PY) return fail(PWGS_EINVAL, "unknown semantics");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(c->scratch.alloc((size_t)c->D + 1));
-    pair_llh_kernel<<<(c->D + 127) / 128, 128, 0, c->stream>>>(data_view(c), tree_view(c), 1, c->D, nullptr, 0, nullptr, semantics,
+    pair_llh_kernel<<<(c->D + 127) / 128, 128, 0, c->stream>>>(data_view(c), tree_view(c), 1, c->D, nullptr, 0, nullptr, 0, semantics,
                                                                kLogTinyMh, kLogTinyPy, kLogQuarter, c->scratch.p);
     CUDA_TRY(cudaGetLastError());
     sum_kernel<<<1, 1024, 0, c->stream>>>(c->D, c->scratch.p, c->scratch.p + c->D);

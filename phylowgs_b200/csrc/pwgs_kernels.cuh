@@ -288,14 +288,19 @@ __device__ double datum_ll_at(const DataView &dv, const TreeView &tv, int j, int
 // mode 0: pairs (rows[r], cols[c]) -> out[r*n_cols + c]     (block of the datum x node grid; cols NULL = all K nodes)
 // mode 1: pairs (j, node_of_datum[j]) for all j -> out[j]    (terms of the complete-data likelihood)
 __global__ void pair_llh_kernel(DataView dv, TreeView tv, int mode, int n_rows, const int *__restrict__ rows, int n_cols,
-                                const int *__restrict__ cols, int semantics, double log_tiny_mh, double log_tiny_py, double log_quarter,
+                                const int *__restrict__ cols, int col_major, int semantics, double log_tiny_mh, double log_tiny_py, double log_quarter,
                                 double *__restrict__ out)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = mode == 0 ? (size_t)n_rows * n_cols : (size_t)n_rows;
     if (i >= total) return;
     int j, s;
-    if (mode == 0) { j = rows[i / n_cols]; s = (int)(i % n_cols); if (cols) s = cols[s]; }   // cols == NULL: all K nodes
+    if (mode == 0) {
+        // row-major: out[r][c], neighbouring threads = neighbouring nodes; column-major: out[c][r], neighbouring threads = data
+        const size_t r = col_major ? i % n_rows : i / n_cols;
+        j = rows[r]; s = (int)(col_major ? i / n_rows : i % n_cols);
+        if (cols) s = cols[s];                                   // cols == NULL: all K nodes
+    }
     else { j = (int)i; s = tv.node_of_datum[j]; }
     out[i] = datum_ll_at(dv, tv, j, s, semantics, log_tiny_mh, log_tiny_py, log_quarter);
 }

@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import SEM_MH, SEM_PY, PwgsError, check, f64, i32, p_f64, p_i32  # noqa: F401
+from ._lib import LAYOUT_COLS, SEM_MH, SEM_PY, PwgsError, check, f64, i32, p_f64, p_i32  # noqa: F401
 
 
 class Engine:
@@ -80,18 +80,20 @@ class Engine:
         return dict(phi=phi, pi=pi, ratio=ratio.value, llh=llh.value, kernel_ms=ms.value)
 
     # ------------------------------------------------------------------ likelihoods
-    def llh_rows(self, rows, semantics=SEM_PY):
+    def llh_rows(self, rows, semantics=SEM_PY, col_major=False):
+        """-> [n_rows, K]; col_major: [K, n_rows] (one contiguous column per node, PWGS_LAYOUT_COLS)."""
         rows = i32(rows)
-        out = np.zeros((len(rows), self.K))
-        check(_lib.load().pwgs_llh_rows(self._h, len(rows), p_i32(rows), int(semantics), p_f64(out)))
+        out = np.empty((self.K, len(rows)) if col_major else (len(rows), self.K))
+        check(_lib.load().pwgs_llh_rows(self._h, len(rows), p_i32(rows), int(semantics) | (LAYOUT_COLS if col_major else 0), p_f64(out)))
         return out
 
-    def llh_block(self, rows, cols, semantics=SEM_PY):
+    def llh_block(self, rows, cols, semantics=SEM_PY, col_major=False):
         rows, cols = i32(rows), i32(cols)
-        out = np.zeros((len(rows), len(cols)))
+        out = np.empty((len(cols), len(rows)) if col_major else (len(rows), len(cols)))
         if out.size == 0:
             return out
-        check(_lib.load().pwgs_llh_block(self._h, len(rows), p_i32(rows), len(cols), p_i32(cols), int(semantics), p_f64(out)))
+        check(_lib.load().pwgs_llh_block(self._h, len(rows), p_i32(rows), len(cols), p_i32(cols),
+                                         int(semantics) | (LAYOUT_COLS if col_major else 0), p_f64(out)))
         return out
 
     def total_llh(self, semantics=SEM_PY):

@@ -66,6 +66,13 @@ class Backend(object):
     def mh(self, iters, std, seed, stream):
         raise NotImplementedError
 
+    # column-major forms ([node][row]: one contiguous column per node, what the assignment sweep reads)
+    def llh_rows_t(self, rows):
+        return np.ascontiguousarray(self.llh_rows(rows).T)
+
+    def llh_block_t(self, rows, cols):
+        return np.ascontiguousarray(self.llh_block(rows, cols).T)
+
     # -- shared glue
     def sync_tree(self, tssb):
         nodes, parent, nod, phi, pi = flatten_tree(tssb)
@@ -101,6 +108,12 @@ class GpuBackend(Backend):
 
     def llh_block(self, rows, cols):
         return self.engine.llh_block(rows, cols, SEM_PY)
+
+    def llh_rows_t(self, rows):
+        return self.engine.llh_rows(rows, SEM_PY, col_major=True)     # written column-major by the kernel: no transpose on the host
+
+    def llh_block_t(self, rows, cols):
+        return self.engine.llh_block(rows, cols, SEM_PY, col_major=True)
 
     def total_llh(self):
         return self.engine.total_llh(SEM_PY)

@@ -75,7 +75,11 @@ class _Grid(object):
     def __init__(self, tssb):
         self.tssb = t = tssb
         self.backend = b = t.backend
-        self.nodes = list(b.sync_tree(t))                   # preorder; the device tree now equals the host tree
+        from .backend import flatten_tree
+        nodes, parent, nod, phi, pi = flatten_tree(t)       # preorder
+        b.set_tree_arrays(parent, nod, phi, pi)             # the device tree now equals the host tree
+        b.nodes = nodes
+        self.nodes = list(nodes)
         self.uid = {id(nd): k for k, nd in enumerate(self.nodes)}
         self.entries = []                                   # tree entry dict of every node, same indexing
         stack = [t.root]
@@ -84,14 +88,19 @@ class _Grid(object):
             self.entries.append(e)
             stack.extend(reversed(e["children"]))
         assert all(e["node"] is nd for e, nd in zip(self.entries, self.nodes))
-        self.nod = np.zeros(t.num_data, dtype=np.int32)
-        for k, nd in enumerate(self.nodes):
-            if nd.data:
-                self.nod[list(nd.data)] = k
+        self.nod = nod
+        # the tree as arrays, kept in step with the spawns of the sweep (rows appended; a spawn also changes its parent's pi):
+        # re-reading every node object at each of the ~100 refreshes of a sweep cost more than the refreshes themselves
+        K = len(self.nodes)
+        cap = max(64, 2 * K)
+        self._parent = np.zeros(cap, dtype=np.int32)
+        self._phi = np.zeros((cap, phi.shape[1]))
+        self._pi = np.zeros((cap, phi.shape[1]))
+        self._parent[:K], self._phi[:K], self._pi[:K] = parent, phi, pi
         self.spawned = getattr(t, "n_spawned", 0)
         self.calls = 1
-        full = b.llh_rows(np.arange(t.num_data, dtype=np.int32))
-        self.cols = [np.ascontiguousarray(full[:, k]) for k in range(full.shape[1])]
+        self._full = b.llh_rows_t(np.arange(t.num_data, dtype=np.int32))     # [K][D]: the columns are views, no copies
+        self.cols = [self._full[k] for k in range(self._full.shape[0])]
         if not hasattr(t, "_ssms_of_cnv"):                  # CNV datum index -> SSM datum indices linked to it
             m = {}
             for d in t.data:
@@ -100,26 +109,35 @@ class _Grid(object):
             t._ssms_of_cnv = {k: np.array(sorted(v), dtype=np.int32) for k, v in m.items()}
 
     def _push_tree(self):
-        nodes = self.nodes
-        parent = np.array([-1 if nd.parent() is None else self.uid[id(nd.parent())] for nd in nodes], dtype=np.int32)
-        phi = np.array([np.asarray(nd.params, dtype=np.float64).reshape(-1) for nd in nodes])
-        pi = np.array([np.asarray(nd.pi, dtype=np.float64).reshape(-1) for nd in nodes])
-        self.backend.set_tree_arrays(parent, self.nod, phi, pi)
+        K = len(self.nodes)
+        self.backend.set_tree_arrays(self._parent[:K], self.nod, self._phi[:K], self._pi[:K])
 
     def register(self, entry):
         """A node spawned during the sweep gets the next index."""
-        self.uid[id(entry["node"])] = len(self.nodes)
-        self.nodes.append(entry["node"])
+        nd = entry["node"]
+        k = len(self.nodes)
+        self.uid[id(nd)] = k
+        self.nodes.append(nd)
         self.entries.append(entry)
+        if k >= len(self._parent):                          # grow
+            cap = 2 * len(self._parent)
+            self._parent = np.resize(self._parent, cap)
+            self._phi = np.resize(self._phi, (cap, self._phi.shape[1]))
+            self._pi = np.resize(self._pi, (cap, self._pi.shape[1]))
+        pk = self.uid[id(nd.parent())]
+        self._parent[k] = pk
+        self._phi[k] = np.asarray(nd.params, dtype=np.float64).reshape(-1)
+        self._pi[k] = np.asarray(nd.pi, dtype=np.float64).reshape(-1)
+        self._pi[pk] = np.asarray(nd.parent().pi, dtype=np.float64).reshape(-1)   # the spawn took its pi out of the parent's
 
     def fetch_new_columns(self, n, first):
         """Columns of nodes[first:] for the data still to be visited (rows n..)."""
         self._push_tree()
         cols = np.arange(first, len(self.nodes), dtype=np.int32)
-        block = self.backend.llh_block(np.arange(n, self.tssb.num_data, dtype=np.int32), cols)
+        block = self.backend.llh_block_t(np.arange(n, self.tssb.num_data, dtype=np.int32), cols)
         for i in range(len(cols)):
             col = np.empty(self.tssb.num_data)
-            col[n:] = block[:, i]
+            col[n:] = block[i]
             self.cols.append(col)
         self.spawned = getattr(self.tssb, "n_spawned", 0)
         self.calls += 1
@@ -144,9 +162,9 @@ class _Grid(object):
             return
         self._push_tree()
         K = len(self.nodes)
-        block = self.backend.llh_block(rows, np.arange(K, dtype=np.int32))
+        block = self.backend.llh_block_t(rows, np.arange(K, dtype=np.int32))
         for k in range(K):
-            self.cols[k][rows] = block[:, k]
+            self.cols[k][rows] = block[k]
         self.calls += 1
 
     def get(self, n, node):
@@ -229,8 +247,13 @@ class _Sweep(C.Structure):
 def resample_assignments_native(tssb):
     from .. import _lib
     from .model import _entry
+    import time
+    timing = os.environ.get("PWGS_SWEEP_TIMING") == "1"
+    t_start = time.perf_counter()
+    t_cb = [0.0, 0, 0]                                  # seconds inside callbacks, spawn events, CNV moves
     lib = _lib.load()
     grid = _Grid(tssb)
+    t_grid = time.perf_counter()
     N, K0 = tssb.num_data, len(grid.nodes)
     cap_nodes, cap_spawn = K0 + 8192, 8192
     stream = UniformStream(tssb.rng, _uniform_block(tssb))
@@ -269,6 +292,7 @@ def resample_assignments_native(tssb):
         state["mirrored"] = sw.n_spawned
 
     def on_spawn(_user, n):
+        t0 = time.perf_counter()
         try:
             first = len(grid.nodes)
             mirror_spawns()
@@ -279,8 +303,12 @@ def resample_assignments_native(tssb):
         except BaseException as e:          # noqa: B902 - must not propagate through the C frame
             failure.append(e)
             return -1
+        finally:
+            t_cb[0] += time.perf_counter() - t0
+            t_cb[1] += 1
 
     def on_cnv_move(_user, n):
+        t0 = time.perf_counter()
         try:
             grid.nod[:] = assign                            # the device needs the CNV's new node (and may as well get the rest)
             grid.after_cnv_move(int(n), int(n))
@@ -288,6 +316,9 @@ def resample_assignments_native(tssb):
         except BaseException as e:          # noqa: B902
             failure.append(e)
             return -1
+        finally:
+            t_cb[0] += time.perf_counter() - t0
+            t_cb[2] += 1
 
     def refill(_user):
         try:
@@ -308,7 +339,9 @@ def resample_assignments_native(tssb):
     sw.spawn_parent, sw.spawn_stick = sp_parent.ctypes.data_as(_ip), sp_stick.ctypes.data_as(_dp)
     sw.spawn_main, sw.spawn_frac = sp_main.ctypes.data_as(_dp), sp_frac.ctypes.data_as(_dp)
     sw.user, sw.on_spawn, sw.on_cnv_move, sw.refill = None, cb_spawn, cb_cnv, cb_refill
+    t_setup = time.perf_counter()
     rc = lib.pwgs_resample_assignments(C.cast(C.byref(sw), C.c_void_p))
+    t_native = time.perf_counter()
     if failure:
         raise failure[0]
     if rc != 0:
@@ -324,6 +357,12 @@ def resample_assignments_native(tssb):
         tssb.assignments[n] = new
         tssb.data[n].node = new
     tssb.last_grid_refreshes = grid.calls
+    if timing:
+        t_end = time.perf_counter()
+        sys.stderr.write("sweep timing: grid %.1f ms, setup %.1f ms, native sweep %.1f ms (of which callbacks %.1f ms: %d spawn events, "
+                         "%d CNV moves), mirror-back %.1f ms; K %d -> %d\n"
+                         % (1e3 * (t_grid - t_start), 1e3 * (t_setup - t_grid), 1e3 * (t_native - t_setup), 1e3 * t_cb[0], t_cb[1], t_cb[2],
+                            1e3 * (t_end - t_native), K0, len(grid.nodes)))
 
 
 def resample_assignments(tssb):

@@ -65,6 +65,11 @@ def test_llh_rows(case, oracle, sem):
     got = eng.llh_rows(rows, sem)
     assert got.shape == want.shape
     assert rel(got, want) < RTOL
+    # column-major output (PWGS_LAYOUT_COLS): the same numbers, one contiguous column per node
+    got_t = eng.llh_rows(rows, sem, col_major=True)
+    assert got_t.shape == (tree.K, len(rows)) and np.array_equal(got_t, got.T)
+    cols = np.array([tree.K - 1, 0], dtype=np.int32)
+    assert np.array_equal(eng.llh_block(rows[:7], cols, sem, col_major=True), eng.llh_block(rows[:7], cols, sem).T)
 
 
 def test_bundled_golden_cases(oracle, gpu_lib):
