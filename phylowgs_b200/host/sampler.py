@@ -349,13 +349,19 @@ def resample_assignments_native(tssb):
     mirror_spawns()
     for _ in range(sw.n_shrunk):
         sys.stderr.write("Slice sampler shrank down.  Keep current state.\n")
-    for n in np.nonzero(assign != before)[0]:
-        n = int(n)
-        old, new = grid.nodes[before[n]], grid.nodes[assign[n]]
-        old.remove_datum(n)
-        new.add_datum(n)
-        tssb.assignments[n] = new
-        tssb.data[n].node = new
+    # mirror the moves back into the Python objects: set operations per node, two stores per moved datum
+    changed = np.nonzero(assign != before)[0]
+    if len(changed):
+        for key, op in ((before[changed], "difference_update"), (assign[changed], "update")):
+            order = np.argsort(key, kind="stable")
+            ks, starts = np.unique(key[order], return_index=True)
+            for k, chunk in zip(ks.tolist(), np.split(changed[order], starts[1:])):
+                getattr(grid.nodes[k].data, op)(chunk.tolist())
+        nodes, assignments, data = grid.nodes, tssb.assignments, tssb.data
+        for n, k in zip(changed.tolist(), assign[changed].tolist()):
+            nd = nodes[k]
+            assignments[n] = nd
+            data[n].node = nd
     tssb.last_grid_refreshes = grid.calls
     if timing:
         t_end = time.perf_counter()
