@@ -207,6 +207,7 @@ def tree_sample_rate(s, device, iterations=6):
     import pickle
     from oracle import oracle as O                     # only to write the workload in the reference's file formats
     from phylowgs_b200.host import evolve as E
+    from phylowgs_b200.host import fastpickle
     from phylowgs_b200.host.backend import GpuBackend
     from phylowgs_b200.host.model import TSSB, alleles, boundbeta
     from phylowgs_b200.host.params import metropolis
@@ -242,7 +243,7 @@ def tree_sample_rate(s, device, iterations=6):
             mh_std /= 2.0
         tssb.resample_sticks(); tssb.resample_stick_orders(); tssb.resample_hypers()
         tssb.complete_data_log_likelihood(); t.append(time.perf_counter())
-        pickle.dumps(tssb, protocol=2); t.append(time.perf_counter())
+        fastpickle.dumps(tssb); t.append(time.perf_counter())              # what evolve.do_mcmc calls (protocol-2 pickle of the tree)
         times.append(t[-1] - t[0])
         parts.append(np.diff(t))
     backend.close()

@@ -25,7 +25,7 @@ from datetime import datetime
 
 import numpy as np
 
-from . import model
+from . import fastpickle, model
 from .backend import GpuBackend
 from .model import TSSB, Datum, alleles, boundbeta
 from .params import get_c_fnames, metropolis
@@ -306,6 +306,7 @@ def resume_existing_run(state_manager, backup_manager, safe_to_exit, run_succeed
 def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, state, tree_writer, codes, n_ssms, n_cnvs, ntps,
             tmp_dir_parent, workdir="."):
     samples_fn = os.path.join(workdir, "mcmc_samples.txt")
+    plain_pickle = os.environ.get("PWGS_PLAIN_PICKLE", "0") == "1"
     on_status = config.get("on_status")           # multievolve --in-process reads the progress here instead of from a pipe
     start_iter = state["last_iteration"] + 1
     unwritten, sample_times = [], []
@@ -359,7 +360,8 @@ def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, 
         else:
             logmsg(" ".join("%s=%s" % kv for kv in status.items()))
 
-        unwritten.append((pickle.dumps(tssb, protocol=2), iteration, last_llh))
+        # protocol-2 pickle of the tree (util2.py:250-262), assembled from cached per-datum fragments; PWGS_PLAIN_PICKLE=1 = pickle.dumps
+        unwritten.append((pickle.dumps(tssb, protocol=2) if plain_pickle else fastpickle.dumps(tssb), iteration, last_llh))
         state["rand_state"] = tssb.rng.get_state()
         state["last_iteration"] = iteration
         if len([c for c in tssb.root["children"] if c["node"].has_data()]) > 1:

@@ -1,0 +1,204 @@
+"""Protocol-2 pickle of a TSSB, byte-compatible with what `pickle.dumps(tssb, protocol=2)` readers expect (util2.py:250-262,
+TreeReader util2.py:264-343), produced several times faster.
+
+What costs in the plain pickler is the list of D `Datum` objects: ~15 attributes each, all constant over the chain except the
+reference to the datum's node.  So the tree is pickled in two parts:
+
+  * everything but `tssb.data` goes through the ordinary C pickler (nodes, sticks, the assignment list of node references, ...)
+    with a placeholder string where the data list belongs; the pickler's memo then tells under which index every node object
+    and the TSSB itself can be referenced;
+  * the data list is written by hand from cached byte fragments, one per datum (its constant attributes, pickled once with a
+    memo-less pickler), joined with a `LONG_BINGET <node>` per datum.  Memo indices of the hand-written part start at 2^16, above
+    the ordinary pickler's (a tree with more memo entries than that falls back).  Datums that other datums point to (the CNVs of an SSM's `cnv` list) are defined in a preamble
+    (`... POP`) so that every reference follows its definition.
+
+The result unpickles (Python 2 or 3, plain `pickle.load`) to the same object graph: same attributes, `datum.node` the very node
+object of `tssb.assignments`, `datum.tssb` the tree, `cnv` links pointing at the CNV datums of the same list.  Anything
+unexpected (an attribute that is not a plain value, a reference cycle between datums) falls back to the ordinary pickler."""
+import io
+import pickle
+import struct
+
+_PLACEHOLDER = "\x00pwgs-b200 data list goes here\x00"
+_BASE = 1 << 16                                          # first memo index of the hand-written part: above the ordinary pickler's
+                                                         # (checked), small because Python 3's unpickler keeps its memo in an array
+
+_MARK, _POP, _STOP = b"(", b"0", b"."
+_EMPTY_LIST, _APPENDS, _EMPTY_DICT, _SETITEMS, _BUILD = b"]", b"e", b"}", b"u", b"b"
+_EMPTY_TUPLE, _NEWOBJ, _NONE, _TUPLE3 = b")", b"\x81", b"N", b"\x87"
+
+
+def _put(i):
+    return b"r" + struct.pack("<I", i)                  # LONG_BINPUT
+
+
+def _get(i):
+    return (b"h" + struct.pack("<B", i)) if i < 256 else (b"j" + struct.pack("<I", i))     # BINGET / LONG_BINGET
+
+
+_buf = io.BytesIO()
+_fast = pickle.Pickler(_buf, protocol=2)
+_fast.fast = True                                        # no memo: no PUT opcodes that could collide with the main stream
+_small = {}
+
+
+def _plain(value):
+    """Pickle body of a plain value (numbers, strings, lists / tuples of them) without memo traffic, header or STOP."""
+    if type(value) is int and -1 <= value < 256:         # the common case, cached
+        body = _small.get(value)
+        if body is not None:
+            return body
+    _buf.seek(0)
+    _buf.truncate()
+    _fast.dump(value)
+    body = _buf.getvalue()
+    assert body[:2] == b"\x80\x02" and body[-1:] == _STOP
+    body = body[2:-1]
+    if type(value) is int and -1 <= value < 256:
+        _small[value] = body
+    return body
+
+
+def _is_plain(v, depth=0):
+    if v is None or isinstance(v, (bool, int, float, str)):
+        return True
+    if isinstance(v, (list, tuple)) and depth < 3:
+        return all(_is_plain(x, depth + 1) for x in v)
+    return False
+
+
+class TreePickler(object):
+    """Caches the constant fragment of every datum of one chain's data list."""
+
+    VARIABLE = ("node", "tssb")
+
+    def __init__(self, data):
+        self.data = data
+        self.ok = True
+        self.keys = {}                                   # attribute name -> memo index
+        pos = {id(d): i for i, d in enumerate(data)}
+        self.pos = pos
+        try:
+            self.cls_global = b"c" + type(data[0]).__module__.encode() + b"\n" + type(data[0]).__name__.encode() + b"\n"
+            referenced = set()
+            frags = [self._fragment(i, referenced) for i in range(len(data))]
+            self._key("tssb")
+            self.frags = frags
+            self.referenced = sorted(referenced)
+        except (ValueError, KeyError, TypeError, AttributeError):
+            self.ok = False
+
+    def _fragment(self, i, referenced):
+        """Everything of datum i up to the value of its `node` attribute."""
+        data, d = self.data, self.data[i]
+        if type(d) is not type(data[0]):
+            raise ValueError("mixed datum classes")
+        parts = [_get(_BASE), _EMPTY_TUPLE, _NEWOBJ, _put(_BASE + 1 + i), _EMPTY_DICT, _MARK]
+        for key, v in d.__dict__.items():
+            if key in self.VARIABLE:
+                continue
+            parts.append(self._key(key))
+            if key == "cnv":
+                parts.append(_EMPTY_LIST)
+                if v:
+                    parts.append(_MARK)
+                    for other, c1, c2 in v:
+                        j = self.pos[id(other)]
+                        if data[j].cnv:
+                            raise ValueError("linked datum has links of its own")
+                        referenced.add(j)
+                        parts += [_get(_BASE + 1 + j), _plain(c1), _plain(c2), _TUPLE3]
+                    parts.append(_APPENDS)
+            elif _is_plain(v):
+                parts.append(_plain(v))
+            else:
+                raise ValueError("attribute %s of a datum is not a plain value" % key)
+        parts.append(self._key("node"))
+        return b"".join(parts)
+
+    def _fresh(self):
+        """The cache assumes the datums' own attributes never change; spot-check a few."""
+        n = len(self.data)
+        try:
+            n_keys = len(self.keys)
+            ok = all(self._fragment(i, set()) == self.frags[i] for i in {0, n // 2, n - 1})
+            return ok and len(self.keys) == n_keys
+        except (ValueError, KeyError, TypeError, AttributeError):
+            return False
+
+    def _key(self, name):
+        if name not in self.keys:
+            self.keys[name] = _BASE + 1 + len(self.data) + len(self.keys)
+        return _get(self.keys[name])
+
+    def dumps(self, tssb):
+        data = tssb.data
+        if not self.ok or data is not self.data or not self._fresh():
+            return pickle.dumps(tssb, protocol=2)
+        # 1. everything but the data list -- which goes last, so that every node is defined before the list refers to it
+        buf = io.BytesIO()
+        pk = pickle.Pickler(buf, protocol=2)
+        saved = tssb.__dict__
+        stub = dict(saved)
+        stub.pop("data")
+        stub["data"] = _PLACEHOLDER
+        tssb.__dict__ = stub
+        try:
+            pk.dump(tssb)
+        finally:
+            tssb.__dict__ = saved
+        main = buf.getvalue()
+        memo = pk.memo.copy()                            # id(obj) -> (index, obj)
+        marker = _plain(_PLACEHOLDER)
+        at = main.find(marker)
+        if at < 0 or main.find(marker, at + 1) >= 0 or id(tssb) not in memo or len(memo) >= _BASE:
+            return pickle.dumps(tssb, protocol=2)
+        end = at + len(marker)
+        if main[end:end + 1] == b"q":                    # the placeholder string's own BINPUT / LONG_BINPUT
+            end += 2
+        elif main[end:end + 1] == b"r":
+            end += 5
+        # 2. the data list
+        noderef = {}
+        tail = self._key("tssb") + _get(memo[id(tssb)][0]) + _SETITEMS + _BUILD
+        out = [self.cls_global, _put(_BASE), _POP]
+        for name, idx in self.keys.items():
+            out += [_plain(name), _put(idx), _POP]
+        frags = self.frags
+
+        def ref(d):
+            nd = d.__dict__.get("node")
+            if nd is None:
+                return _NONE
+            r = noderef.get(id(nd))
+            if r is None:
+                m = memo.get(id(nd))
+                if m is None:
+                    raise KeyError("node of a datum is not part of the tree")
+                r = noderef[id(nd)] = _get(m[0])
+            return r
+        try:
+            for j in self.referenced:                    # define the linked-to datums first
+                out += [frags[j], ref(data[j]), tail, _POP]
+            out += [_EMPTY_LIST, _MARK]
+            defined = set(self.referenced)
+            for i, d in enumerate(data):
+                if i in defined:
+                    out.append(_get(_BASE + 1 + i))
+                else:
+                    out.append(frags[i])
+                    out.append(ref(d))
+                    out.append(tail)
+            out.append(_APPENDS)
+        except KeyError:
+            return pickle.dumps(tssb, protocol=2)
+        return main[:at] + b"".join(out) + main[end:]
+
+
+def dumps(tssb):
+    """pickle.dumps(tssb, protocol=2) for a chain's tree, with the per-chain cache kept on the data list's owner."""
+    tp = tssb.__dict__.get("_tree_pickler")
+    if tp is None or tp.data is not tssb.data:
+        tp = TreePickler(tssb.data)
+        tssb.__dict__["_tree_pickler"] = tp
+    return tp.dumps(tssb)
