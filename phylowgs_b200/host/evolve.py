@@ -148,8 +148,10 @@ class StateManager(object):
         self.initial_state_fn = os.path.join(workdir, self.default_initial_state_fn)
 
     def _dump(self, state, fn):
+        tssb = state.get("tssb")
+        plain = tssb is None or os.environ.get("PWGS_PLAIN_PICKLE", "0") == "1"
         with open(fn, "wb") as f:
-            pickle.dump(state, f, protocol=2)
+            f.write(pickle.dumps(state, protocol=2) if plain else fastpickle.dumps(tssb, root=state))
 
     def write_state(self, state):
         self._dump(state, self.last_state_fn)

@@ -131,10 +131,12 @@ class TreePickler(object):
             self.keys[name] = _BASE + 1 + len(self.data) + len(self.keys)
         return _get(self.keys[name])
 
-    def dumps(self, tssb):
+    def dumps(self, tssb, root=None):
+        """Pickle of `root` (default: the tree itself), an object graph that contains the tree -- e.g. the chain's state dict."""
+        root = tssb if root is None else root
         data = tssb.data
         if not self.ok or data is not self.data or not self._fresh():
-            return pickle.dumps(tssb, protocol=2)
+            return pickle.dumps(root, protocol=2)
         # 1. everything but the data list -- which goes last, so that every node is defined before the list refers to it
         buf = io.BytesIO()
         pk = pickle.Pickler(buf, protocol=2)
@@ -144,7 +146,7 @@ class TreePickler(object):
         stub["data"] = _PLACEHOLDER
         tssb.__dict__ = stub
         try:
-            pk.dump(tssb)
+            pk.dump(root)
         finally:
             tssb.__dict__ = saved
         main = buf.getvalue()
@@ -152,53 +154,45 @@ class TreePickler(object):
         marker = _plain(_PLACEHOLDER)
         at = main.find(marker)
         if at < 0 or main.find(marker, at + 1) >= 0 or id(tssb) not in memo or len(memo) >= _BASE:
-            return pickle.dumps(tssb, protocol=2)
+            return pickle.dumps(root, protocol=2)
         end = at + len(marker)
         if main[end:end + 1] == b"q":                    # the placeholder string's own BINPUT / LONG_BINPUT
             end += 2
         elif main[end:end + 1] == b"r":
             end += 5
-        # 2. the data list
-        noderef = {}
+        # 2. the data list: per datum [fragment, reference to its node, tail], assembled with slice assignments (no Python-level
+        #    work per datum beyond reading its `node`)
         tail = self._key("tssb") + _get(memo[id(tssb)][0]) + _SETITEMS + _BUILD
         out = [self.cls_global, _put(_BASE), _POP]
         for name, idx in self.keys.items():
             out += [_plain(name), _put(idx), _POP]
         frags = self.frags
-
-        def ref(d):
-            nd = d.__dict__.get("node")
-            if nd is None:
-                return _NONE
-            r = noderef.get(id(nd))
-            if r is None:
-                m = memo.get(id(nd))
-                if m is None:
-                    raise KeyError("node of a datum is not part of the tree")
-                r = noderef[id(nd)] = _get(m[0])
-            return r
+        noderef = {id(None): _NONE}
+        for oid, (idx, obj) in memo.items():
+            noderef[oid] = _get(idx)
         try:
-            for j in self.referenced:                    # define the linked-to datums first
-                out += [frags[j], ref(data[j]), tail, _POP]
-            out += [_EMPTY_LIST, _MARK]
-            defined = set(self.referenced)
-            for i, d in enumerate(data):
-                if i in defined:
-                    out.append(_get(_BASE + 1 + i))
-                else:
-                    out.append(frags[i])
-                    out.append(ref(d))
-                    out.append(tail)
-            out.append(_APPENDS)
-        except KeyError:
-            return pickle.dumps(tssb, protocol=2)
+            refs = [noderef[id(d.node)] for d in data]   # KeyError: a datum's node is not part of the tree
+        except (KeyError, AttributeError):
+            return pickle.dumps(root, protocol=2)
+        for j in self.referenced:                        # define the linked-to datums first
+            out += [frags[j], refs[j], tail, _POP]
+        out += [_EMPTY_LIST, _MARK]
+        n = len(data)
+        body = [tail] * (3 * n)
+        body[0::3] = frags
+        body[1::3] = refs
+        for j in self.referenced:                        # already defined: a reference instead of a second definition
+            body[3 * j], body[3 * j + 1], body[3 * j + 2] = _get(_BASE + 1 + j), b"", b""
+        out += body
+        out.append(_APPENDS)
         return main[:at] + b"".join(out) + main[end:]
 
 
-def dumps(tssb):
-    """pickle.dumps(tssb, protocol=2) for a chain's tree, with the per-chain cache kept on the data list's owner."""
+def dumps(tssb, root=None):
+    """pickle.dumps(root or tssb, protocol=2) for a chain's tree (or an object holding it, like the chain's state dict), with the
+    per-chain cache kept on the tree."""
     tp = tssb.__dict__.get("_tree_pickler")
     if tp is None or tp.data is not tssb.data:
         tp = TreePickler(tssb.data)
         tssb.__dict__["_tree_pickler"] = tp
-    return tp.dumps(tssb)
+    return tp.dumps(tssb, root)

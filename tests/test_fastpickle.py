@@ -115,3 +115,13 @@ def test_fallback_when_a_datum_is_not_plain():
     blob = fastpickle.dumps(t)
     assert not t.__dict__["_tree_pickler"].ok
     assert np.array_equal(pickle.loads(blob).data[3].extra, np.arange(3))
+
+
+def test_state_dict_holding_the_tree():
+    """state.last.pickle: a dict with the tree inside (evolve.py StateManager) goes through the same splice."""
+    t = make_tree()
+    state = {"tssb": t, "last_iteration": 7, "mh_std": 200.0, "trace": np.arange(5.0), "glist": [d.name for d in t.data]}
+    got = pickle.loads(fastpickle.dumps(t, root=state))
+    want = pickle.loads(pickle.dumps(state, protocol=2))
+    assert set(got) == set(want) and got["last_iteration"] == 7 and np.array_equal(got["trace"], want["trace"]) and got["glist"] == want["glist"]
+    same_graph(got["tssb"], want["tssb"])
