@@ -12,6 +12,7 @@ import csv
 import json
 import os
 import pickle
+import queue
 import shutil
 import signal
 import sys
@@ -147,11 +148,19 @@ class StateManager(object):
         self.last_state_fn = os.path.join(workdir, self.default_last_state_fn)
         self.initial_state_fn = os.path.join(workdir, self.default_initial_state_fn)
 
-    def _dump(self, state, fn):
+    @staticmethod
+    def dumps(state):
         tssb = state.get("tssb")
         plain = tssb is None or os.environ.get("PWGS_PLAIN_PICKLE", "0") == "1"
+        return pickle.dumps(state, protocol=2) if plain else fastpickle.dumps(tssb, root=state)
+
+    def write_state_bytes(self, blob):
+        with open(self.last_state_fn, "wb") as f:
+            f.write(blob)
+
+    def _dump(self, state, fn):
         with open(fn, "wb") as f:
-            f.write(pickle.dumps(state, protocol=2) if plain else fastpickle.dumps(tssb, root=state))
+            f.write(self.dumps(state))
 
     def write_state(self, state):
         self._dump(state, self.last_state_fn)
@@ -194,6 +203,54 @@ class TreeWriter(object):
         with self._open() as z:
             for blob, idx, llh in serialized_trees:
                 z.writestr("%s_%s_%s" % ("burnin" if idx < 0 else "tree", idx, llh), blob)
+
+
+class AsyncWriter(object):
+    """A chain's checkpoint writes (mcmc_samples.txt, trees.zip, state.last.pickle, backups) on one background thread, in order,
+    one checkpoint in flight at a time: deflating ten trees takes as long as a tree sample or two, releases the GIL, and has no
+    reason to stall the chain.  What is written is fixed when the job is submitted (the trees and the state are already bytes).
+    A signal handler calls stop_and_drain(): no new write starts afterwards and the one in flight is finished, so the files
+    are as consistent as with in-line writes (trees first, then the state that refers to them)."""
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._idle = threading.Event()
+        self._idle.set()
+        self._stopping = False
+        self._error = None
+        self._jobs = queue.Queue()
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def _run(self):
+        while True:
+            job = self._jobs.get()
+            try:
+                job()
+            except BaseException as e:      # noqa: B902 - handed to the chain's thread by wait()
+                self._error = e
+            finally:
+                self._idle.set()
+
+    def wait(self):
+        self._idle.wait()
+        if self._error is not None:
+            e, self._error = self._error, None
+            raise e
+
+    def submit(self, job):
+        self.wait()
+        with self._lock:
+            stopping = self._stopping
+            if not stopping:
+                self._idle.clear()
+                self._jobs.put(job)
+        if stopping:                        # the process is about to exit on a signal: never start another write
+            threading.Event().wait()
+
+    def stop_and_drain(self):
+        with self._lock:
+            self._stopping = True
+        self._idle.wait()
 
 
 # ------------------------------------------------------------------ the chain
@@ -309,6 +366,8 @@ def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, 
             tmp_dir_parent, workdir="."):
     samples_fn = os.path.join(workdir, "mcmc_samples.txt")
     plain_pickle = os.environ.get("PWGS_PLAIN_PICKLE", "0") == "1"
+    writer = None if os.environ.get("PWGS_SYNC_WRITES", "0") == "1" else AsyncWriter()
+    config["writer"] = writer
     on_status = config.get("on_status")           # multievolve --in-process reads the progress here instead of from a pipe
     start_iter = state["last_iteration"] + 1
     unwritten, sample_times = [], []
@@ -377,14 +436,24 @@ def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, 
         write_backup = iteration % state["write_backups_every"] == 0 and iteration != start_iter
         write_state = iteration % state["write_state_every"] == 0
         if write_backup or write_state or iteration == state["num_samples"] - 1:
-            with open(samples_fn, "a") as f:
-                f.write("\n".join("%s\t%s\t%s" % (it, llh, dt) for (_, it, llh), dt in zip(unwritten, sample_times)) + "\n")
-            tree_writer.write_trees(unwritten)
-            state_manager.write_state(state)
-            unwritten, sample_times = [], []
-            if write_backup:
-                backup_manager.save_backup()
+            rows = "\n".join("%s\t%s\t%s" % (it, llh, dt) for (_, it, llh), dt in zip(unwritten, sample_times)) + "\n"
+            trees, state_blob = unwritten, state_manager.dumps(state)     # fixed now; the chain goes on while they are written
 
+            def checkpoint(rows=rows, trees=trees, state_blob=state_blob, write_backup=write_backup):
+                with open(samples_fn, "a") as f:
+                    f.write(rows)
+                tree_writer.write_trees(trees)
+                state_manager.write_state_bytes(state_blob)
+                if write_backup:
+                    backup_manager.save_backup()
+            if writer is None:
+                checkpoint()
+            else:
+                writer.submit(checkpoint)
+            unwritten, sample_times = [], []
+
+    if writer is not None:
+        writer.wait()
     backup_manager.remove_backup()
     safe_to_exit.set()
     run_succeeded.set()
@@ -467,6 +536,8 @@ def main(argv=None):
     def on_signal(signo, _frame):
         logmsg("Signal %s received." % signo, sys.stderr)
         safe_to_exit.wait()
+        if config.get("writer") is not None:
+            config["writer"].stop_and_drain()
         remove_tmp_files(config["tmp_dir"])
         logmsg("Exiting now.")
         sys.exit(3)

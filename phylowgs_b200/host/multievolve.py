@@ -161,6 +161,8 @@ def run_chains_in_process(chain_dirs, ssm_fn, cnv_fn, seeds, other_args, devices
         logmsg("Signal %s received." % signo, sys.stderr)
         for _, safe, _, config in chains:
             safe.wait()
+            if config.get("writer") is not None:
+                config["writer"].stop_and_drain()
         for _, _, _, config in chains:
             evolve.remove_tmp_files(config["tmp_dir"])
         logmsg("Exiting now.")

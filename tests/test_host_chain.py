@@ -113,3 +113,38 @@ def test_native_sweep_equals_python_sweep(monkeypatch, tmp_path, files):
     wa, na = trees[0].get_mixture()
     wb, nb = trees[1].get_mixture()
     assert wa == wb and [sorted(n.data) for n in na] == [sorted(n.data) for n in nb]
+
+
+def test_async_writer_runs_jobs_in_order_reports_errors_and_drains():
+    import threading
+    import time
+    from phylowgs_b200.host.evolve import AsyncWriter
+    w, log = AsyncWriter(), []
+    for k in range(5):
+        w.submit(lambda k=k: (time.sleep(0.01), log.append(k)))
+    w.wait()
+    assert log == [0, 1, 2, 3, 4]
+
+    def boom():
+        raise OSError("disk full")
+    w.submit(boom)
+    with pytest.raises(OSError):
+        w.wait()
+    w.submit(lambda: log.append("after"))                 # the error was delivered once; the writer keeps working
+    w.wait()
+    assert log[-1] == "after"
+    # a signal handler drains: the write in flight finishes, nothing new starts
+    started, release = threading.Event(), threading.Event()
+    w.submit(lambda: (started.set(), release.wait(5), log.append("in flight")))
+    started.wait(5)
+    t = threading.Thread(target=w.stop_and_drain)
+    t.start()
+    time.sleep(0.05)
+    assert t.is_alive()                                    # still draining
+    release.set()
+    t.join(5)
+    assert not t.is_alive() and log[-1] == "in flight"
+    late = threading.Thread(target=lambda: w.submit(lambda: log.append("late")), daemon=True)
+    late.start()
+    late.join(0.3)
+    assert late.is_alive() and log[-1] == "in flight"      # blocked for good: the process is exiting
