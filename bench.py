@@ -185,7 +185,9 @@ def ncu_traffic_bytes():
     import glob
     import re
     best = None
-    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_mh_kernel_ncu_full.txt"))):
+    def natural(fn):                                                        # r01_v10 after r01_v9
+        return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", os.path.basename(fn))]
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_mh_kernel_ncu_full.txt")), key=natural):
         rd = wr = None
         for line in open(fn):
             m = re.match(r"dram__bytes_(read|write)\.sum\s+(\S+)\s+(\S+)", line)
