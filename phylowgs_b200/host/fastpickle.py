@@ -18,6 +18,7 @@ unexpected (an attribute that is not a plain value, a reference cycle between da
 import io
 import pickle
 import struct
+import threading
 
 _PLACEHOLDER = "\x00pwgs-b200 data list goes here\x00"
 _BASE = 1 << 16                                          # first memo index of the hand-written part: above the ordinary pickler's
@@ -36,22 +37,25 @@ def _get(i):
     return (b"h" + struct.pack("<B", i)) if i < 256 else (b"j" + struct.pack("<I", i))     # BINGET / LONG_BINGET
 
 
-_buf = io.BytesIO()
-_fast = pickle.Pickler(_buf, protocol=2)
-_fast.fast = True                                        # no memo: no PUT opcodes that could collide with the main stream
+_tls = threading.local()                                 # one memo-less pickler per thread: chains may share a process
 _small = {}
 
 
 def _plain(value):
     """Pickle body of a plain value (numbers, strings, lists / tuples of them) without memo traffic, header or STOP."""
-    if type(value) is int and -1 <= value < 256:         # the common case, cached
+    if type(value) is int and -1 <= value < 256:         # the common case, cached (idempotent: safe to race on)
         body = _small.get(value)
         if body is not None:
             return body
-    _buf.seek(0)
-    _buf.truncate()
-    _fast.dump(value)
-    body = _buf.getvalue()
+    buf = getattr(_tls, "buf", None)
+    if buf is None:
+        buf = _tls.buf = io.BytesIO()
+        _tls.pickler = pickle.Pickler(buf, protocol=2)
+        _tls.pickler.fast = True                         # no memo: no PUT opcodes that could collide with the main stream
+    buf.seek(0)
+    buf.truncate()
+    _tls.pickler.dump(value)
+    body = buf.getvalue()
     assert body[:2] == b"\x80\x02" and body[-1:] == _STOP
     body = body[2:-1]
     if type(value) is int and -1 <= value < 256:

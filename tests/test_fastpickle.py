@@ -125,3 +125,34 @@ def test_state_dict_holding_the_tree():
     want = pickle.loads(pickle.dumps(state, protocol=2))
     assert set(got) == set(want) and got["last_iteration"] == 7 and np.array_equal(got["trace"], want["trace"]) and got["glist"] == want["glist"]
     same_graph(got["tssb"], want["tssb"])
+
+
+def test_fragment_building_is_thread_safe():
+    """Chains of one process (multievolve --in-process) build their caches at the same time."""
+    import threading
+    trees = [make_tree(ssm=os.path.join(cases.GOLDEN, "emptysim.4.100.50.ssm.txt"), cnv=os.devnull, seed=s) for s in range(4)]
+    want = [pickle.dumps(t, protocol=2) for t in trees]
+    blobs, errors = [None] * len(trees), []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                trees[i].__dict__.pop("_tree_pickler", None)          # rebuild the cache every time
+                blobs[i] = fastpickle.dumps(trees[i])
+        except Exception as e:                                         # noqa: BLE001
+            errors.append(repr(e))
+    import sys
+    old = sys.getswitchinterval()
+    sys.setswitchinterval(1e-6)                                        # hand the GIL over as often as possible
+    try:
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(len(trees))]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join(120)
+    finally:
+        sys.setswitchinterval(old)
+    assert not errors, errors
+    for t, blob, w in zip(trees, blobs, want):
+        assert t.__dict__["_tree_pickler"].ok
+        same_graph(pickle.loads(blob), pickle.loads(w))
