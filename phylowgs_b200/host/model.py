@@ -388,15 +388,35 @@ class TSSB(object):
                 raise Exception("Slice sampler shrank to zero!")
 
     def resample_hypers(self, dp_alpha=True, alpha_decay=True, dp_gamma=True):
-        """tssb.py:245-316."""
+        """tssb.py:245-316.  The sticks do not change while the hyper-parameters are slice-sampled, so they are gathered once
+        and every likelihood evaluation is one vector expression (the reference walks the tree per evaluation)."""
+        mains, depths, sticks, stack = [], [], [], [(self.root, 0)]
+        while stack:
+            entry, depth = stack.pop()
+            if self.min_depth <= depth:
+                mains.append(float(entry["main"]))
+                depths.append(depth)
+            for i, c in enumerate(entry["children"]):
+                sticks.append(float(np.ravel(entry["sticks"][i])[0]))
+                stack.append((c, depth + 1))
+        log1m_main = np.log(1.0 - np.array(mains))
+        depths = np.array(depths, dtype=float)
+        log1m_stick = np.log(1.0 - np.array(sticks)) if sticks else np.zeros(0)
+
+        def beta1_llh(log1m, b):
+            # sum of log Beta(x; 1, b) = gammaln(1+b) - gammaln(b) + (b-1) log(1-x)   (betapdfln with a = 1)
+            return float(np.sum(gammaln(1.0 + b) - gammaln(b) + (b - 1.0) * log1m))
+
+        def alpha_llh(a, decay):
+            return beta1_llh(log1m_main, (decay ** depths) * a)
+
         if dp_alpha:
-            self.dp_alpha = self._slice_1d(lambda v: self.dp_alpha_llh(v, self.alpha_decay), self.dp_alpha,
-                                           self.min_dp_alpha, self.max_dp_alpha)
+            self.dp_alpha = self._slice_1d(lambda v: alpha_llh(v, self.alpha_decay), self.dp_alpha, self.min_dp_alpha, self.max_dp_alpha)
         if alpha_decay:
-            self.alpha_decay = self._slice_1d(lambda v: self.dp_alpha_llh(self.dp_alpha, v), self.alpha_decay,
+            self.alpha_decay = self._slice_1d(lambda v: alpha_llh(self.dp_alpha, v), self.alpha_decay,
                                               self.min_alpha_decay, self.max_alpha_decay)
         if dp_gamma:
-            self.dp_gamma = self._slice_1d(self.dp_gamma_llh, self.dp_gamma, self.min_dp_gamma, self.max_dp_gamma)
+            self.dp_gamma = self._slice_1d(lambda v: beta1_llh(log1m_stick, np.float64(v)), self.dp_gamma, self.min_dp_gamma, self.max_dp_gamma)
 
     # ------------------------------------------------------------------ the two likelihood-bound call sites (device)
     def resample_assignments(self):
