@@ -48,6 +48,20 @@ def test_evolve_cli_outputs(gpu_lib, tmp_path):
     for fn in ("state.initial.pickle", "state.last.pickle"):
         assert os.path.exists(os.path.join(out, fn))
     assert "Run succeeded." in r.stdout
+    # the members are protocol-2 pickles a plain reader loads (util2.py:264-343): consistent trees, data attached
+    import pickle
+    from phylowgs_b200.host.evolve import install_pickle_aliases
+    install_pickle_aliases()
+    with zipfile.ZipFile(os.path.join(out, "trees.zip")) as z:
+        for name in [n for n in names if n.startswith("tree_")][:3]:
+            blob = z.read(name)
+            assert blob[:2] == b"\x80\x02"
+            t = pickle.loads(blob)
+            nodes = t.get_nodes()
+            assert sum(len(nd.data) for nd in nodes) == t.num_data == len(t.data) == 12
+            for n, d in enumerate(t.data):
+                assert d.tssb is t and d.node is t.assignments[n] and n in d.node.data
+            assert [c.id for c, _, _ in t.data[2].cnv] == ["c0"] and t.data[2].cnv[0][0] is t.data[11]
 
 
 def test_evolve_resumes_after_sigterm_and_reproduces_the_uninterrupted_chain(gpu_lib, tmp_path):
