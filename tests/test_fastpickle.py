@@ -156,3 +156,11 @@ def test_fragment_building_is_thread_safe():
     for t, blob, w in zip(trees, blobs, want):
         assert t.__dict__["_tree_pickler"].ok
         same_graph(pickle.loads(blob), pickle.loads(w))
+
+
+def test_pure_python_unpickler_reads_it_too():
+    """The pure-Python unpickler (dict memo, opcode by opcode -- the closest stand-in here for Python 2's pickle module)."""
+    import io
+    t = make_tree(n_children=4, seed=12)
+    got = pickle._Unpickler(io.BytesIO(fastpickle.dumps(t))).load()
+    same_graph(got, pickle.loads(pickle.dumps(t, protocol=2)))
