@@ -37,7 +37,10 @@ def run_chain(tssb, n_ssms, n_cnvs, iterations, mh_iters, seed, mh_std=100.0):
             nd.id = i
         E.set_node_height(tssb)
         E.set_path_from_root_to_node(tssb)
-        E.map_datum_to_node(tssb)
+        if it == 0:
+            E.map_datum_to_node(tssb)
+        else:                                              # evolve.do_mcmc relies on the sweeps keeping datum.node in step
+            assert all(d.node is tssb.assignments[n] for n, d in enumerate(tssb.data))
         pos = {id(nd): k for k, nd in enumerate(nodes)}
         assign = np.array([pos[id(nd)] for nd in tssb.assignments])
         acc = float(metropolis(tssb, mh_iters, mh_std, 0, n_ssms, n_cnvs, "", "", seed, ntps, ".", stream=it))
