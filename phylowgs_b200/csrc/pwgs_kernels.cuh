@@ -870,15 +870,17 @@ __device__ __noinline__ bool mh_epoch_start(const MhParams &p, const MhSmem &S, 
 }
 
 // One chain = cpc co-resident CTAs (cooperative launch).  Every CTA keeps the node table in shared memory, evaluates its slice
-// of the data for a batch of nb speculative proposals, and the per-CTA partial sums meet in a per-chain barrier.
+// of the data (whole warp rounds, dealt by cost: plan_partition in pwgs_api.cu) for a batch of nb speculative proposals, adds
+// its partial sums to the chain's running integer totals and meets the other CTAs in a per-chain barrier; every CTA then reads
+// the same totals and takes the same accept / reject decisions.
 // "Prefetching" MH: proposals for iterations it0..it0+nb-1 are all drawn from the current state; the first accepted one ends
 // the batch and the later ones are discarded, which is exactly the sequential chain because a rejected iteration leaves the
 // state untouched and each iteration owns its random substream.  The batch size adapts to the acceptance rate (doubling after
-// all-reject batches, shrinking after accepts).  Proposals are drawn ahead of time under the assumption that the batches in
-// flight reject everything: the first two batches after every accept are drawn redundantly by every CTA (the second one while
-// the first one's barrier is in flight); from the third on, each (proposal, sample) is drawn ONCE per chain by the producer
-// warp of its owner CTA two batches ahead and travels through a ring in global memory under the chain barrier's release /
-// acquire.  Chains with few CTAs keep drawing locally.
+// all-reject batches up to 128, to 256 after MH_WIDE_AFTER of them in a row; shrinking after accepts).  Proposals are drawn
+// ahead of time under the assumption that the batches in flight reject everything: each (proposal, sample) is drawn ONCE per
+// chain -- the first two batches after an accept by all warps of the chain (mh_epoch_start, one extra barrier), every later
+// batch by the producer warp of its owner CTA two batches ahead (mh_ring_tasks) -- and travels through a ring in global memory
+// under the chain barrier's release / acquire.  Chains with few CTAs draw locally in every CTA.
 template <bool STAGED>
 __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, int cpc)
 {
