@@ -180,6 +180,14 @@ int pwgs_fp64_peak(int device, double *dfma_per_s);
  * a warp round {plain, cnv1, cnv2, cnv3}.  Out: round_slot [ceil(M/32)] first slot of each CNV round in the CTA-major list,
  * cta_nc [cpc] CNV-affected SSMs per CTA, pstart [6][cpc+1] plain range boundaries per class, the two slice strides.  Used by the
  * CPU test-suite to check that every datum is walked exactly once per proposal whatever the shape. */
+/* Diagnostics, host code only (no device needed): the grid likelihood of pwgs_llh_rows -- the very function the kernel runs,
+ * compiled for the host -- on caller-owned arrays (layouts as in pwgs_create / pwgs_set_tree): out[r*K + k].  The CPU test-suite
+ * holds it against the oracle, so the device code's logic is checked where there is no GPU. */
+int pwgs_selftest_llh_host(int n_ssm, int n_cnv, int ntps, const int32_t *a, const int32_t *d, const double *mu_r, const double *mu_v,
+                           const int32_t *cnv_ptr, const int32_t *cnv_idx, const int32_t *cnv_c1, const int32_t *cnv_c2,
+                           int K, const int32_t *parent, const int32_t *node_of_datum, const double *phi, const double *pi,
+                           int n_rows, const int32_t *rows, int semantics, double *out);
+
 int pwgs_plan_partition(int cpc, int M, const int32_t *n_states, int Dp, int ncls, const int32_t *w,
                         int32_t *round_slot, int32_t *cta_nc, int32_t *pstart, int32_t *cchunk, int32_t *pchunk);
 

@@ -37,6 +37,8 @@ SIGNATURES = {
     "pwgs_resample_assignments": (C.c_int, [C.c_void_p]),      # struct pwgs_sweep*, see host/sampler.py::_Sweep
     "pwgs_math_selftest": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p]),
     "pwgs_fp64_peak": (C.c_int, [C.c_int, _f64p]),
+    "pwgs_selftest_llh_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _f64p, _i32p, _i32p, _i32p, _i32p,
+                                         C.c_int, _i32p, _i32p, _f64p, _f64p, C.c_int, _i32p, C.c_int, _f64p]),
     "pwgs_plan_partition": (C.c_int, [C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
 }
 

@@ -79,6 +79,8 @@ struct pwgs_ctx {
     CnvWork work;
     // ---- MH
     DevBuf<unsigned long long> sums;
+    DevBuf<double> phisub;
+    int root = 0;
     DevBuf<double> ring, phi_out, pi_out, llh_out, scratch;
     DevBuf<unsigned long long> counter, prof;
     bool opt_prof = false;
@@ -96,6 +98,57 @@ static const double kLogTinyMh = log(pow(10, -99));   // mh.hpp:100
 static const double kLogTinyPy = log(1e-99);          // data.py:57
 static const double kLogQuarter = log(0.25);          // mh.hpp:97
 
+// Host-side preparation of a tree (pwgs_set_tree; also the host self-test of the grid likelihood): validation, depth, Euler
+// tour (ancestor tests are two integer compares), children-first order, subtree sums of pi.
+struct HostTree {
+    int root = -1;
+    std::vector<int> depth, tin, tout, order;
+    std::vector<double> phisub;
+};
+static bool host_tree_prep(int K, int T, const int32_t *parent, const double *pi, HostTree &ht, std::string &err)
+{
+    // ---- validate: exactly one root, in-range parents, no cycles
+    int root = -1;
+    for (int k = 0; k < K; k++) {
+        if (parent[k] < 0) { if (root >= 0) { err = "more than one root"; return false; } root = k; }
+        else if (parent[k] >= K || parent[k] == k) { err = "parent index out of range at node " + std::to_string(k); return false; }
+    }
+    if (root < 0) { err = "no root (parent == -1) in tree"; return false; }
+    std::vector<int> &depth = ht.depth;
+    depth.assign(K, -1);
+    depth[root] = 0;
+    for (int k = 0; k < K; k++) {
+        int v = k, steps = 0;
+        std::vector<int> path;
+        while (depth[v] < 0) { path.push_back(v); v = parent[v]; if (++steps > K) { err = "cycle in parent array"; return false; } }
+        int dd = depth[v];
+        for (int i = (int)path.size() - 1; i >= 0; i--) depth[path[i]] = ++dd;
+    }
+    // ---- Euler tour (children in increasing index) and the children-first accumulation order
+    std::vector<std::vector<int>> kids(K);
+    for (int k = 0; k < K; k++) if (parent[k] >= 0) kids[parent[k]].push_back(k);
+    ht.tin.assign(K, 0); ht.tout.assign(K, 0);
+    std::vector<int> stack{root}, it(K, 0);
+    int clock = 0;
+    ht.tin[root] = clock++;
+    while (!stack.empty()) {
+        int v = stack.back();
+        if (it[v] < (int)kids[v].size()) { int ch = kids[v][it[v]++]; ht.tin[ch] = clock++; stack.push_back(ch); }
+        else { ht.tout[v] = clock++; stack.pop_back(); }
+    }
+    ht.order.resize(K);
+    for (int k = 0; k < K; k++) ht.order[k] = k;
+    std::stable_sort(ht.order.begin(), ht.order.end(), [&](int x, int y) { return depth[x] > depth[y]; });
+    // ---- subtree sums of pi, children before parents (deterministic; what the sparse grid sums multiply)
+    ht.phisub.assign(pi, pi + (size_t)K * T);
+    for (int i = 0; i < K; i++) {
+        const int k = ht.order[i];
+        if (parent[k] >= 0) for (int tp = 0; tp < T; tp++) ht.phisub[(size_t)parent[k] * T + tp] += ht.phisub[(size_t)k * T + tp];
+    }
+    ht.root = root;
+    return true;
+}
+
 static DataView data_view(pwgs_ctx *c)
 {
     DataView v;
@@ -110,6 +163,7 @@ static TreeView tree_view(pwgs_ctx *c)
     v.K = c->K; v.T = c->T;
     v.parent = c->parent.p; v.depth = c->depth.p; v.tin = c->tin.p; v.tout = c->tout.p;
     v.phi = c->phi.p; v.pi = c->pi.p; v.node_of_datum = c->node_of_datum.p;
+    v.phisub = c->phisub.p; v.root = c->root;
     return v;
 }
 
@@ -141,7 +195,7 @@ int pwgs_destroy(pwgs_ctx *c)
     c->phi.release(); c->pi.release(); c->coef.release();
     c->code_tmp.release(); c->enode_tmp.release(); c->pos.release(); c->w_a.release(); c->w_d.release(); c->w_code.release();
     c->w_enode.release(); c->overflow.release(); c->plan.release(); c->ecoef_tmp.release(); c->w_ecoef.release(); c->w_lbc.release(); c->w_mu_r.release();
-    c->sums.release(); c->ring.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
+    c->sums.release(); c->phisub.release(); c->ring.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
     c->counter.release(); c->prof.release(); c->acc_out.release(); c->abort_flag.release(); c->cols.release(); c->rows.release(); c->plist.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -296,41 +350,17 @@ int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node
     if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
     if (K <= 0 || K > 65535) return fail(PWGS_EINVAL, "K must be in 1..65535");
     if (!parent || !node_of_datum || !phi || !pi) return fail(PWGS_EINVAL, "NULL array");
-    // ---- validate: exactly one root, in-range parents, no cycles
-    int root = -1;
-    for (int k = 0; k < K; k++) {
-        if (parent[k] < 0) { if (root >= 0) return fail(PWGS_EINVAL, "more than one root"); root = k; }
-        else if (parent[k] >= K || parent[k] == k) return fail(PWGS_EINVAL, "parent index out of range at node " + std::to_string(k));
-    }
-    if (root < 0) return fail(PWGS_EINVAL, "no root (parent == -1) in tree");
-    std::vector<int> depth(K, -1);
-    depth[root] = 0;
-    for (int k = 0; k < K; k++) {
-        int v = k, steps = 0;
-        std::vector<int> path;
-        while (depth[v] < 0) { path.push_back(v); v = parent[v]; if (++steps > K) return fail(PWGS_EINVAL, "cycle in parent array"); }
-        int dd = depth[v];
-        for (int i = (int)path.size() - 1; i >= 0; i--) depth[path[i]] = ++dd;
+    HostTree ht;
+    {
+        std::string err;
+        if (!host_tree_prep(K, c->T, parent, pi, ht, err)) return fail(PWGS_EINVAL, err);
     }
     for (size_t i = 0; i < (size_t)K * c->T; i++)
         if (!(phi[i] >= 0.0 && phi[i] <= 1.000001 && pi[i] >= 0.0 && pi[i] <= 1.000001))
             return fail(PWGS_EINVAL, "phi and pi must lie in [0,1] (node " + std::to_string(i / c->T) + ")");
     for (int j = 0; j < c->D; j++)
         if (node_of_datum[j] < 0 || node_of_datum[j] >= K) return fail(PWGS_EINVAL, "node_of_datum out of range at datum " + std::to_string(j));
-    // ---- Euler tour (children in increasing index) and the children-first accumulation order
-    std::vector<std::vector<int>> kids(K);
-    for (int k = 0; k < K; k++) if (parent[k] >= 0) kids[parent[k]].push_back(k);
-    std::vector<int> tin(K), tout(K), stack{root}, it(K, 0);
-    int clock = 0;
-    tin[root] = clock++;
-    while (!stack.empty()) {
-        int v = stack.back();
-        if (it[v] < (int)kids[v].size()) { int ch = kids[v][it[v]++]; tin[ch] = clock++; stack.push_back(ch); }
-        else { tout[v] = clock++; stack.pop_back(); }
-    }
-    std::vector<int> order(K);
-    for (int k = 0; k < K; k++) order[k] = k;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return depth[x] > depth[y]; });
+    const std::vector<int> &depth = ht.depth, &tin = ht.tin, &tout = ht.tout, &order = ht.order;
 
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
@@ -344,6 +374,8 @@ int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node
     CUDA_TRY(c->node_of_datum.upload(node_of_datum, c->D, s));
     CUDA_TRY(c->phi.upload(phi, (size_t)K * T, s));
     CUDA_TRY(c->pi.upload(pi, (size_t)K * T, s));
+    CUDA_TRY(c->phisub.upload(ht.phisub.data(), (size_t)K * T, s));
+    c->root = ht.root;
     CUDA_TRY(c->phi_out.alloc((size_t)K * T));
     CUDA_TRY(c->pi_out.alloc((size_t)K * T));
     if (c->Dp > 0) {
@@ -849,6 +881,38 @@ int pwgs_plan_partition(int cpc, int M, const int32_t *n_states, int Dp, int ncl
     for (int i = 0; i < cpc; i++) cta_nc[i] = P.cta_nc[i];
     for (size_t i = 0; i < P.pstart.size(); i++) pstart[i] = P.pstart[i];
     *cchunk = P.cchunk; *pchunk = P.pchunk;
+    return PWGS_OK;
+}
+
+int pwgs_selftest_llh_host(int n_ssm, int n_cnv, int ntps, const int32_t *a, const int32_t *d, const double *mu_r, const double *mu_v,
+                           const int32_t *cnv_ptr, const int32_t *cnv_idx, const int32_t *cnv_c1, const int32_t *cnv_c2,
+                           int K, const int32_t *parent, const int32_t *node_of_datum, const double *phi, const double *pi,
+                           int n_rows, const int32_t *rows, int semantics, double *out)
+{
+    if (n_ssm < 0 || n_cnv < 0 || ntps < 1 || K < 1 || n_rows < 0 || !a || !d || !mu_r || !mu_v || !parent || !node_of_datum || !phi || !pi ||
+        (n_rows > 0 && (!rows || !out)))
+        return fail(PWGS_EINVAL, "pwgs_selftest_llh_host: bad argument");
+    if (semantics != PWGS_SEM_MH && semantics != PWGS_SEM_PY) return fail(PWGS_EINVAL, "unknown semantics");
+    const int D = n_ssm + n_cnv;
+    HostTree ht;
+    std::string err;
+    if (!host_tree_prep(K, ntps, parent, pi, ht, err)) return fail(PWGS_EINVAL, err);
+    std::vector<double> lbc((size_t)D * ntps);
+    for (size_t i = 0; i < lbc.size(); i++) lbc[i] = lgamma((double)d[i] + 1.0) - lgamma((double)a[i] + 1.0) - lgamma((double)(d[i] - a[i]) + 1.0);
+    std::vector<int32_t> zero_ptr(n_ssm + 1, 0);
+    DataView dv;
+    dv.n_ssm = n_ssm; dv.n_cnv = n_cnv; dv.T = ntps;
+    dv.a = a; dv.d = d; dv.mu_r = mu_r; dv.mu_v = mu_v; dv.lbc = lbc.data();
+    dv.cnv_ptr = cnv_ptr ? cnv_ptr : zero_ptr.data(); dv.cnv_idx = cnv_idx; dv.cnv_c1 = cnv_c1; dv.cnv_c2 = cnv_c2;
+    TreeView tv;
+    tv.K = K; tv.T = ntps;
+    tv.parent = parent; tv.depth = ht.depth.data(); tv.tin = ht.tin.data(); tv.tout = ht.tout.data();
+    tv.phi = phi; tv.pi = pi; tv.node_of_datum = node_of_datum; tv.phisub = ht.phisub.data(); tv.root = ht.root;
+    for (int r = 0; r < n_rows; r++) {
+        if (rows[r] < 0 || rows[r] >= D) return fail(PWGS_EINVAL, "row index out of range");
+        for (int k = 0; k < K; k++)
+            out[(size_t)r * K + k] = datum_ll_at(dv, tv, rows[r], k, semantics, kLogTinyMh, kLogTinyPy, kLogQuarter);
+    }
     return PWGS_OK;
 }
 

@@ -20,6 +20,8 @@ struct TreeView {
     const double *phi;   // [K*T]
     const double *pi;    // [K*T]
     const int *node_of_datum;  // [D]
+    const double *phisub; // [K*T] subtree sums of pi (children-first on the host, pwgs_set_tree): what the sparse grid sums multiply
+    int root;
 };
 
 struct DataView {
@@ -30,14 +32,14 @@ struct DataView {
     const int *cnv_ptr, *cnv_idx, *cnv_c1, *cnv_c2;
 };
 
-__device__ __forceinline__ bool anc_or_self(const TreeView &t, int u, int v)
+__host__ __device__ __forceinline__ bool anc_or_self(const TreeView &t, int u, int v)
 {
     return t.tin[u] <= t.tin[v] && t.tout[v] <= t.tout[u];
 }
 
 // data.py:128-134 == params.py:174-180: deepest ancestor-or-self of node k hosting one of SSM j's CNVs;
 // two CNVs in the same node -> the first link in file order (strict '>' keeps it).
-__device__ __forceinline__ int most_recent_cnv(const DataView &d, const TreeView &t, int j, int k)
+__host__ __device__ __forceinline__ int most_recent_cnv(const DataView &d, const TreeView &t, int j, int k)
 {
     int best = -1, best_depth = -1;
     for (int l = d.cnv_ptr[j]; l < d.cnv_ptr[j + 1]; l++) {
@@ -49,7 +51,7 @@ __device__ __forceinline__ int most_recent_cnv(const DataView &d, const TreeView
 
 // The four-way case split of data.py:71-109 / params.py:131-158: integer (nr,nv) that node k contributes to the
 // four genome states of SSM j sitting in node s.
-__device__ __forceinline__ void state_coefs(const DataView &d, const TreeView &t, int j, int s, int k, int nr[4], int nv[4])
+__host__ __device__ __forceinline__ void state_coefs(const DataView &d, const TreeView &t, int j, int s, int k, int nr[4], int nv[4])
 {
     bool in_sub = anc_or_self(t, s, k);
     int l = most_recent_cnv(d, t, j, k);
@@ -63,8 +65,8 @@ __device__ __forceinline__ void state_coefs(const DataView &d, const TreeView &t
         for (int q = 0; q < 4; q++) { nr[q] = tt; nv[q] = 0; }
     } else {
         int c1 = d.cnv_c1[l], c2 = d.cnv_c2[l], tt = c1 + c2;
-        nr[2] = nr[3] = max(0, tt - 1);
-        nv[2] = nv[3] = min(1, tt);
+        nr[2] = nr[3] = tt > 1 ? tt - 1 : 0;          // max(0, t-1), min(1, t)
+        nv[2] = nv[3] = tt < 1 ? tt : 1;
         int cnv_node = t.node_of_datum[d.n_ssm + d.cnv_idx[l]];
         if (anc_or_self(t, s, cnv_node)) { nr[0] = c1; nv[0] = c2; nr[1] = c2; nv[1] = c1; }
         else { nr[0] = nr[1] = nr[2]; nv[0] = nv[1] = nv[2]; }
@@ -252,13 +254,13 @@ __constant__ double c_logw[5] = {0.0, 0.0, 0.6931471805599453, 1.098612288668109
 
 // ------------------------------------------------------------------ likelihood terms
 // util.cpp:16-18 / util2.py:30
-__device__ __forceinline__ double log_binomial_likelihood(int x, int n, double mu)
+__host__ __device__ __forceinline__ double log_binomial_likelihood(int x, int n, double mu)
 {
     return (double)x * log(mu) + (double)(n - x) * log(1.0 - mu);
 }
 
 // util.cpp:35-43 over exactly four values
-__device__ __forceinline__ double logsumexp4(const double x[4])
+__host__ __device__ __forceinline__ double logsumexp4(const double x[4])
 {
     double m = x[0];
 #pragma unroll
@@ -270,7 +272,7 @@ __device__ __forceinline__ double logsumexp4(const double x[4])
 }
 
 // mh.hpp:95-101 for one state
-__device__ __forceinline__ double mh_state_ll(double nr, double nv, int a, int d, double mu_r, double lbc,
+__host__ __device__ __forceinline__ double mh_state_ll(double nr, double nv, int a, int d, double mu_r, double lbc,
                                               double log_quarter, double log_tiny)
 {
     if (nr + nv > 0) {

@@ -224,8 +224,34 @@ __global__ void cnv_scatter_kernel(int M, int T, const int *__restrict__ round_s
 
 // ============================================================================ K2
 // llh of datum j placed in node s under either convention (see oracle/pwgs_oracle.c datum_ll_cpp_at / orc_datum_ll_py).
-__device__ double datum_ll_at(const DataView &dv, const TreeView &tv, int j, int s, int semantics,
-                              double log_tiny_mh, double log_tiny_py, double log_quarter)
+// Sum over all nodes k of pi_k * (nr, nv)_k for the four states of SSM j sitting in node s, at sample tp, WITHOUT walking the
+// nodes: the integer coefficients depend on k only through "is k under s" and "which linked CNV is the most recent above k"
+// (state_coefs), so they change, going down the tree, only at s and at the nodes hosting j's CNVs.  With delta(a) =
+// coef(a) - coef(parent(a)) (coef of the root's parent = 0) the sum is sum_a delta(a) * phisub(a) over those few nodes, phisub
+// being the subtree sums of pi.  O(links^2) per (datum, node) pair instead of O(K * links): the grid of a 100-node tree in the
+// time the dense walk needed for 10 nodes.  (K0c uses the same identity for the MH kernel's work list.)
+__host__ __device__ inline void cnv_state_sums(const DataView &dv, const TreeView &tv, int j, int s, int tp, double nr[4], double nv[4])
+{
+    const int l0 = dv.cnv_ptr[j], L = dv.cnv_ptr[j + 1] - l0, T = dv.T;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { nr[q] = 0.0; nv[q] = 0.0; }
+    for (int i = 0; i < L + 2; i++) {                                       // candidates: root, s, the CNVs' nodes
+        const int a = i == 0 ? tv.root : (i == 1 ? s : tv.node_of_datum[dv.n_ssm + dv.cnv_idx[l0 + i - 2]]);
+        bool seen = false;
+        for (int i2 = 0; i2 < i && !seen; i2++)
+            seen = a == (i2 == 0 ? tv.root : (i2 == 1 ? s : tv.node_of_datum[dv.n_ssm + dv.cnv_idx[l0 + i2 - 2]]));
+        if (seen) continue;
+        int cr[4], cv[4], pr[4] = {0, 0, 0, 0}, pv[4] = {0, 0, 0, 0};
+        state_coefs(dv, tv, j, s, a, cr, cv);
+        if (tv.parent[a] >= 0) state_coefs(dv, tv, j, s, tv.parent[a], pr, pv);
+        const double ph = tv.phisub[a * T + tp];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { nr[q] += ph * (double)(cr[q] - pr[q]); nv[q] += ph * (double)(cv[q] - pv[q]); }
+    }
+}
+
+__host__ __device__ inline double datum_ll_at(const DataView &dv, const TreeView &tv, int j, int s, int semantics,
+                                              double log_tiny_mh, double log_tiny_py, double log_quarter)
 {
     int T = dv.T;
     double mu_r = dv.mu_r[j], mu_v = dv.mu_v[j];
@@ -243,14 +269,8 @@ __device__ double datum_ll_at(const DataView &dv, const TreeView &tv, int j, int
                 (s == tv.node_of_datum[dv.n_ssm + dv.cnv_idx[dv.cnv_ptr[j]]]);
     bool sub0 = false, sub1 = false;
     for (int tp = 0; tp < T; tp++) {
-        double nr[4] = {0, 0, 0, 0}, nv[4] = {0, 0, 0, 0};
-        for (int k = 0; k < tv.K; k++) {
-            int cr[4], cv[4];
-            state_coefs(dv, tv, j, s, k, cr, cv);
-            double p = tv.pi[k * T + tp];
-#pragma unroll
-            for (int q = 0; q < 4; q++) { nr[q] += p * cr[q]; nv[q] += p * cv[q]; }
-        }
+        double nr[4], nv[4];
+        cnv_state_sums(dv, tv, j, s, tp, nr, nv);
         int a = dv.a[j * T + tp], d = dv.d[j * T + tp];
         double lbc = dv.lbc[j * T + tp], llh;
         if (semantics == 0) {                                   // mh.hpp:80-163 after params.py:160-166
