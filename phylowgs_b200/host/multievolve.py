@@ -167,9 +167,10 @@ def run_chains_in_process(chain_dirs, ssm_fn, cnv_fn, seeds, other_args, devices
             evolve.remove_tmp_files(config["tmp_dir"])
         logmsg("Exiting now.")
         os._exit(3)             # the chain threads are mid-iteration by design; nothing is being written (all safe events held)
+    previous = {}
     if threading.current_thread() is threading.main_thread():
-        signal.signal(signal.SIGTERM, on_signal)
-        signal.signal(signal.SIGINT, on_signal)
+        for sig in (signal.SIGTERM, signal.SIGINT):
+            previous[sig] = signal.signal(sig, on_signal)
     for th, _, _, _ in chains:
         th.start()
     while any(th.is_alive() for th, _, _, _ in chains):
@@ -182,6 +183,8 @@ def run_chains_in_process(chain_dirs, ssm_fn, cnv_fn, seeds, other_args, devices
             logmsg("chain={} {}".format(i, " ".join("{}={}".format(k, st[k]) for k in ("status",) + keys)))
     for _, _, _, config in chains:
         evolve.remove_tmp_files(config["tmp_dir"])
+    for sig, handler in previous.items():
+        signal.signal(sig, handler)
     return [0 if ok.is_set() else 1 for _, _, ok, _ in chains]
 
 

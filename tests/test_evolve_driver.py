@@ -88,3 +88,19 @@ def test_sync_writes_and_plain_pickle_switches_give_the_same_files(oracle_backen
     monkeypatch.setenv("PWGS_PLAIN_PICKLE", "1")
     assert run(b, *args)
     assert names(a) == names(b)
+
+
+def test_multievolve_in_process_with_the_oracle(oracle_backend, tmp_path, capsys):
+    """Chains as threads of one process (multievolve --in-process): per-chain directories, status relay, merged trees.zip --
+    and the same chains as the single-chain driver gives for the same seeds."""
+    from phylowgs_b200.host import multievolve as M
+    out = str(tmp_path / "chains")
+    M.main(["-n", "2", "-r", "5", "6", "--gpus", "0", "--in-process", "-O", out, "--ssms", SSM, "--cnvs", CNV,
+            "-B", "2", "-s", "4", "-i", "80", "-S", "2"])
+    text = capsys.readouterr().out
+    assert "chain=1 status=done exit_code=0" in text and "Including chains" in text
+    single = str(tmp_path / "single")
+    assert run(single, "-B", "2", "-s", "4", "-r", "6", "-i", "80", "-S", "2")
+    assert names(os.path.join(out, "chain_1")) == names(single)
+    merged = names(out)
+    assert sum(n.startswith("tree_") for n in merged) in (4, 8) and not any(n.startswith("burnin") for n in merged)
