@@ -321,14 +321,38 @@ class TSSB(object):
                 return
             order = []
             todo = set(i for i, c in enumerate(entry["children"]) if c["node"].has_data())
-            weights = np.diff(np.hstack([0.0, sticks_to_edges(entry["sticks"])]))
+            weights = None
             while todo:
                 u = self.rng.rand()
                 while True:
-                    rest = [i for i in range(entry["sticks"].shape[0]) if i not in order]
-                    w = np.hstack([weights[rest], 1.0 - np.sum(weights)])
-                    w = w / np.sum(w)
-                    pick = int(np.sum(u > np.cumsum(w)))
+                    n_sticks = entry["sticks"].shape[0]
+                    if n_sticks <= 6:
+                        # plain floats for the usual handful of children: the same IEEE operations in the same order as the
+                        # array code below (numpy adds fewer than 8 numbers one after the other; cumprod / cumsum always)
+                        wl, prod, prev, total = [], 1.0, 0.0, 0.0
+                        for st in entry["sticks"].reshape(-1).tolist():
+                            prod = (1.0 - st) if not wl else prod * (1.0 - st)
+                            edge = 1.0 - prod
+                            wl.append(edge - prev)
+                            total += wl[-1]
+                            prev = edge
+                        rest = [i for i in range(n_sticks) if i not in order]
+                        w = [wl[i] for i in rest] + [1.0 - total]
+                        wsum = 0.0
+                        for x in w:
+                            wsum += x
+                        acc, pick = 0.0, 0
+                        if wsum != 0.0:                     # (0/0 in the array code: every comparison false, pick 0)
+                            for x in w:
+                                acc += x / wsum
+                                pick += u > acc
+                    else:
+                        if weights is None or len(weights) != n_sticks:
+                            weights = np.diff(np.hstack([0.0, sticks_to_edges(entry["sticks"])]))
+                        rest = [i for i in range(n_sticks) if i not in order]
+                        w = np.hstack([weights[rest], 1.0 - np.sum(weights)])
+                        w = w / np.sum(w)
+                        pick = int(np.sum(u > np.cumsum(w)))
                     if pick == len(rest):                   # landed beyond the existing sticks: break a new one and retry
                         entry["sticks"] = np.vstack([entry["sticks"], boundbeta(self.rng, 1, self.dp_gamma)])
                         self.n_spawned = getattr(self, "n_spawned", 0) + 1
@@ -336,7 +360,7 @@ class TSSB(object):
                         main = boundbeta(self.rng, 1.0, (self.alpha_decay ** (depth + 1)) * self.dp_alpha) \
                             if self.min_depth <= depth + 1 else 0.0
                         entry["children"].append(_entry(node, main))
-                        weights = np.diff(np.hstack([0.0, sticks_to_edges(entry["sticks"])]))
+                        weights = None
                     else:
                         pick = rest[pick]
                         break
