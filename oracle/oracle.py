@@ -167,6 +167,15 @@ def llh_rows(data, tree, rows, semantics):
     return out
 
 
+def llh_block(data, tree, rows, cols, semantics):
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    out = np.zeros((len(rows), len(cols)))
+    ds, ts = data.cstruct(), tree.cstruct()
+    lib().orc_llh_block(C.byref(ds), C.byref(ts), len(rows), _p(rows, _i), len(cols), _p(cols, _i), int(semantics), _p(out, _d))
+    return out
+
+
 def total_llh(data, tree, semantics):
     ds, ts = data.cstruct(), tree.cstruct()
     return lib().orc_total_llh(C.byref(ds), C.byref(ts), int(semantics))

@@ -262,6 +262,22 @@ void orc_llh_rows(const orc_data *D, const orc_tree *T, int n_rows, const int *r
     free(lbc);
 }
 
+void orc_llh_block(const orc_data *D, const orc_tree *T, int n_rows, const int *rows, int n_cols, const int *cols,
+                   int semantics, double *out)
+{
+    int Dn = D->n_ssm + D->n_cnv, Tn = D->ntps;
+    double *lbc = (double *)malloc(sizeof(double) * Dn * Tn);
+    orc_lbc_table(D, lbc);
+    for (int r = 0; r < n_rows; r++)
+        for (int c = 0; c < n_cols; c++) {
+            int k = cols[c];
+            out[(size_t)r * n_cols + c] = semantics == ORC_SEM_PY
+                ? orc_datum_ll_py(D, T, rows[r], k, T->phi + k * Tn, lbc)
+                : datum_ll_cpp_at(D, T, rows[r], k, T->phi + k * Tn, lbc);
+        }
+    free(lbc);
+}
+
 double orc_total_llh(const orc_data *D, const orc_tree *T, int semantics)
 {
     if (semantics == ORC_SEM_CPP) return orc_multi_param_post(D, T, T->phi, T->pi);

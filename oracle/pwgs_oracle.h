@@ -9,10 +9,11 @@
  * Pinned against: the UNMODIFIED reference mh.cpp/util.cpp compiled into
  * oracle/_ref/libpwgs_ref.so (tests/test_oracle_vs_ref.py when /root/reference or the
  * prebuilt _ref exists) and the committed golden vectors tests/golden/ (JSON files) generated
- * from it (tests/golden/make_golden.py).  The Python-semantics half (data.py) cannot
- * be executed here (Python 2 only): it is pinned only through the cases where
- * data.py and mh.hpp provably coincide => "parity unpinned" for the data.py-only
- * branches (state dropping / re-weighting), as stated in DESIGN.md.
+ * from it (tests/golden/make_golden.py).  The Python-semantics half (data.py:26-126,
+ * params.py:68-171) is pinned against tests/golden/py_vectors.json: outputs of the
+ * reference's own data.py / params.py / tssb.py executed under Python 3 by
+ * oracle/ref_py3.py (declared mechanical patches; tests/golden/make_py_golden.py,
+ * tests/test_py_golden.py).
  *
  * All citations are file:line relative to /root/reference.
  */
@@ -69,6 +70,9 @@ double orc_multi_param_post(const orc_data *D, const orc_tree *T, const double *
 
 /* Rows of the datum x node grid: out[r*K + k] = llh of datum rows[r] if it sat in node k. */
 void   orc_llh_rows(const orc_data *D, const orc_tree *T, int n_rows, const int *rows, int semantics, double *out);
+/* The same for a subset of the nodes: out[r*n_cols + c] = llh of datum rows[r] if it sat in node cols[c]. */
+void   orc_llh_block(const orc_data *D, const orc_tree *T, int n_rows, const int *rows, int n_cols, const int *cols,
+                     int semantics, double *out);
 /* Sum over data of llh(j, node_of_datum[j]) (tssb.py:404-410 data term / mh.cpp:147). */
 double orc_total_llh(const orc_data *D, const orc_tree *T, int semantics);
 

@@ -20,7 +20,7 @@ class OracleBackend(Backend):
         return O.llh_rows(self.data, self.tree, rows, O.SEM_PY)
 
     def llh_block(self, rows, cols):
-        return O.llh_rows(self.data, self.tree, rows, O.SEM_PY)[:, np.asarray(cols, dtype=int)]
+        return O.llh_block(self.data, self.tree, rows, cols, O.SEM_PY)
 
     def total_llh(self):
         return O.total_llh(self.data, self.tree, O.SEM_PY)
