@@ -152,7 +152,7 @@ class StateManager(object):
     def dumps(state):
         tssb = state.get("tssb")
         plain = tssb is None or os.environ.get("PWGS_PLAIN_PICKLE", "0") == "1"
-        return pickle.dumps(state, protocol=2) if plain else fastpickle.dumps(tssb, root=state)
+        return fastpickle.compat_dumps(state) if plain else fastpickle.dumps(tssb, root=state)
 
     def write_state_bytes(self, blob):
         with open(self.last_state_fn, "wb") as f:
@@ -427,7 +427,7 @@ def do_mcmc(state_manager, backup_manager, safe_to_exit, run_succeeded, config, 
             logmsg(" ".join("%s=%s" % kv for kv in status.items()))
 
         # protocol-2 pickle of the tree (util2.py:250-262), assembled from cached per-datum fragments; PWGS_PLAIN_PICKLE=1 = pickle.dumps
-        unwritten.append((pickle.dumps(tssb, protocol=2) if plain_pickle else fastpickle.dumps(tssb), iteration, last_llh))
+        unwritten.append((fastpickle.compat_dumps(tssb) if plain_pickle else fastpickle.dumps(tssb), iteration, last_llh))
         state["rand_state"] = tssb.rng.get_state()
         state["last_iteration"] = iteration
         if len([c for c in tssb.root["children"] if c["node"].has_data()]) > 1:

@@ -1,5 +1,12 @@
-"""Protocol-2 pickle of a TSSB, byte-compatible with what `pickle.dumps(tssb, protocol=2)` readers expect (util2.py:250-262,
-TreeReader util2.py:264-343), produced several times faster.
+"""Protocol-2 pickle of a TSSB in the form the reference's readers expect (util2.py:250-262, TreeReader util2.py:264-343,
+pwgsresults/result_generator.py:11-12), produced several times faster than `pickle.dumps`.
+
+Readable by Python 2 / numpy 1 (`compat_pickler`): numpy >= 2 pickles its arrays and scalars through
+`numpy._core.multiarray._reconstruct / scalar`, a module numpy 1.x does not have.  The stream therefore opens with a hand-written
+preamble that defines those two callables under their numpy-1 names (`numpy.core.multiarray`, still importable under numpy 2)
+at memo slots 0 and 1, and the pickler starts with the same two entries in its memo, so every array and scalar in the stream is a
+`BINGET 0/1` instead of a GLOBAL.  Everything else is protocol-2 material both sides know (tests/test_pickle_compat.py: GLOBAL
+whitelist, opcode whitelist, and the reference's own TreeReader run on the archive).
 
 What costs in the plain pickler is the list of D `Datum` objects: ~15 attributes each, all constant over the chain except the
 reference to the datum's node.  So the tree is pickled in two parts:
@@ -12,7 +19,7 @@ reference to the datum's node.  So the tree is pickled in two parts:
     the ordinary pickler's (a tree with more memo entries than that falls back).  Datums that other datums point to (the CNVs of an SSM's `cnv` list) are defined in a preamble
     (`... POP`) so that every reference follows its definition.
 
-The result unpickles (Python 2 or 3, plain `pickle.load`) to the same object graph: same attributes, `datum.node` the very node
+The result unpickles (plain `pickle.load`) to the same object graph: same attributes, `datum.node` the very node
 object of `tssb.assignments`, `datum.tssb` the tree, `cnv` links pointing at the CNV datums of the same list.  Anything
 unexpected (an attribute that is not a plain value, a reference cycle between datums) falls back to the ordinary pickler."""
 import io
@@ -35,6 +42,37 @@ def _put(i):
 
 def _get(i):
     return (b"h" + struct.pack("<B", i)) if i < 256 else (b"j" + struct.pack("<I", i))     # BINGET / LONG_BINGET
+
+
+def _numpy_reducers():
+    try:
+        from numpy._core import multiarray as m          # numpy >= 2
+    except ImportError:                                  # pragma: no cover - numpy 1.x names them as the readers do
+        from numpy.core import multiarray as m
+    return m._reconstruct, m.scalar
+
+
+# GLOBAL numpy.core.multiarray._reconstruct, BINPUT 0, POP; GLOBAL numpy.core.multiarray.scalar, BINPUT 1, POP
+_NP_PREAMBLE = b"cnumpy.core.multiarray\n_reconstruct\nq\x000cnumpy.core.multiarray\nscalar\nq\x010"
+
+
+def compat_pickler(buf):
+    """A protocol-2 pickler whose output, passed through `compat_finish`, names numpy's reconstructors the numpy-1 way."""
+    pk = pickle.Pickler(buf, protocol=2)
+    pk.memo = {id(f): (i, f) for i, f in enumerate(_numpy_reducers())}
+    return pk
+
+
+def compat_finish(stream):
+    assert stream[:2] == b"\x80\x02"
+    return stream[:2] + _NP_PREAMBLE + stream[2:]
+
+
+def compat_dumps(obj):
+    """pickle.dumps(obj, protocol=2), readable by Python 2 / numpy 1."""
+    buf = io.BytesIO()
+    compat_pickler(buf).dump(obj)
+    return compat_finish(buf.getvalue())
 
 
 _tls = threading.local()                                 # one memo-less pickler per thread: chains may share a process
@@ -140,10 +178,10 @@ class TreePickler(object):
         root = tssb if root is None else root
         data = tssb.data
         if not self.ok or data is not self.data or not self._fresh():
-            return pickle.dumps(root, protocol=2)
+            return compat_dumps(root)
         # 1. everything but the data list -- which goes last, so that every node is defined before the list refers to it
         buf = io.BytesIO()
-        pk = pickle.Pickler(buf, protocol=2)
+        pk = compat_pickler(buf)
         saved = tssb.__dict__
         stub = dict(saved)
         stub.pop("data")
@@ -153,12 +191,12 @@ class TreePickler(object):
             pk.dump(root)
         finally:
             tssb.__dict__ = saved
-        main = buf.getvalue()
+        main = compat_finish(buf.getvalue())
         memo = pk.memo.copy()                            # id(obj) -> (index, obj)
         marker = _plain(_PLACEHOLDER)
         at = main.find(marker)
         if at < 0 or main.find(marker, at + 1) >= 0 or id(tssb) not in memo or len(memo) >= _BASE:
-            return pickle.dumps(root, protocol=2)
+            return compat_dumps(root)
         end = at + len(marker)
         if main[end:end + 1] == b"q":                    # the placeholder string's own BINPUT / LONG_BINPUT
             end += 2
@@ -177,7 +215,7 @@ class TreePickler(object):
         try:
             refs = [noderef[id(d.node)] for d in data]   # KeyError: a datum's node is not part of the tree
         except (KeyError, AttributeError):
-            return pickle.dumps(root, protocol=2)
+            return compat_dumps(root)
         for j in self.referenced:                        # define the linked-to datums first
             out += [frags[j], refs[j], tail, _POP]
         out += [_EMPTY_LIST, _MARK]
