@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpwgs_b200.so")
+# PWGS_LIB: a tuning build of the same library (phylowgs_b200/build.py -D... -o...) for A/B timing of kernel variants
+LIB_PATH = os.environ.get("PWGS_LIB") or os.path.join(HERE, "libpwgs_b200.so")
 
 SEM_MH, SEM_PY = 0, 1
 LAYOUT_COLS = 0x100                      # PWGS_LAYOUT_COLS: column-major output of pwgs_llh_rows / pwgs_llh_block

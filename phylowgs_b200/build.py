@@ -26,20 +26,24 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu -> phylowgs_b200/libpwgs_b200.so.  Returns the library path."""
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """Compile csrc/*.cu -> phylowgs_b200/libpwgs_b200.so.  Returns the library path.
+    `defines` / `out`: tuning builds of kernel variants (-DNAME=VALUE) into another file, loaded with PWGS_LIB=<path>."""
+    out = out or LIB
+    if out == LIB and not force and not needs_build():
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-D" + d for d in defines]
+    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
     import sys
-    print(build_library(force=True, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build_library(force=True, verbose="-v" in sys.argv, defines=defs, out=os.path.abspath(outs[0]) if outs else None))

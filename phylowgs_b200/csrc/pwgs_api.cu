@@ -71,7 +71,7 @@ struct pwgs_ctx {
     int pchunk = 0;
     std::vector<int> plan_counts;                // [cpc][4] rounds per CTA: plain thirds, CNV rounds with 1 / 2 / 3 states (diagnostics)
     const int *pstart_dev = nullptr;
-    int opt_w[4] = {100, 183, 429, 675};             // relative cost of a warp round: plain, CNV-affected with 1 / 2 / 3 merged states
+    int opt_w[4] = {100, 211, 482, 760};             // relative cost of a warp round: plain, CNV-affected with 1 / 2 / 3 merged states
     bool work_valid = false;
     DevBuf<int> code_tmp, enode_tmp, pos, w_a, w_d, w_code, w_enode, overflow, plan;
     DevBuf<int4> ecoef_tmp, w_ecoef;
@@ -556,7 +556,7 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     int B = c->opt_batch;
     int cpc = c->opt_ctas > 0 ? std::min(c->opt_ctas, c->n_sms) : c->n_sms;
     size_t smem = mh_smem_bytes(c->K, c->T, B);
-    while (smem > 160 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B); }
+    while (smem > 176 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B); }
     if (smem > 200 * 1024) return fail(PWGS_ELIMIT, "K*T too large for the shared-memory node table");
     const int collapse = (c->opt_collapse && c->n_classes > 0 && c->Dp > 0) ? c->n_classes : 0;
     { int rc_ = prepare_cnv_work(c, cpc, collapse, mh_group_classes(B)); if (rc_ != PWGS_OK) return rc_; }

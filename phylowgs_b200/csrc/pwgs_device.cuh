@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include "pwgs_tables.cuh"
 
 #define PWGS_MAX_BATCH 256
 #define PWGS_FULL_MASK 0xffffffffu
@@ -73,11 +74,7 @@ __host__ __device__ __forceinline__ void state_coefs(const DataView &d, const Tr
     }
 }
 
-// ------------------------------------------------------------------ straight-line fp64 log / exp
-// The MH kernel evaluates up to eight independent logarithms per datum.  CUDA's log()/exp() carry slow-path branches that
-// keep the compiler from interleaving neighbouring calls; these versions are branch-free (special cases are selects at the
-// end), so independent calls overlap in the FP64 pipe.  Accuracy < 1 ulp (same argument reduction and minimax coefficients
-// as Sun's fdlibm e_log.c, a published algorithm; not GSL, not the reference).
+// ------------------------------------------------------------------ reciprocal seed
 __device__ __forceinline__ double pwgs_rcp_approx(double d)
 {
     double y;
@@ -85,125 +82,65 @@ __device__ __forceinline__ double pwgs_rcp_approx(double d)
     return y;
 }
 
-__device__ __forceinline__ double pwgs_log(double x)
-{
-    int hi = __double2hiint(x), lo = __double2loint(x);
-    const bool sub = hi < 0x00100000;                        // subnormal (or <= 0: fixed up below)
-    const double xs = x * 18014398509481984.0;               // 2^54
-    hi = sub ? __double2hiint(xs) : hi;
-    lo = sub ? __double2loint(xs) : lo;
-    int e = (sub ? -54 : 0) + (hi >> 20) - 1023;
-    hi &= 0x000fffff;
-    const int i = (hi + 0x95f64) & 0x100000;                 // mantissa >= sqrt(2): halve it, bump the exponent
-    hi |= i ^ 0x3ff00000;
-    e += i >> 20;
-    const double f = __hiloint2double(hi, lo) - 1.0;         // m - 1, m in [sqrt(2)/2, sqrt(2))
-    const double d = 2.0 + f;
-    double y = pwgs_rcp_approx(d);                           // ~2^-20; two Newton steps -> full precision
-    double t = fma(-d, y, 1.0);
-    y = fma(y, t, y);
-    t = fma(-d, y, 1.0);
-    y = fma(y, t, y);
-    double q = f * y;
-    q = fma(fma(-d, q, f), y, q);                            // s = f / (2 + f), correctly rounded to < 1 ulp
-    const double z = q * q, w = z * z;
-    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
-                              6.666666666666735130e-01);
-    const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
-    double r = fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(q, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
-    r = (x == 0.0) ? -INFINITY : r;
-    r = (x < 0.0 || x != x) ? NAN : r;
-    r = (x == INFINITY) ? INFINITY : r;
-    return r;
-}
+// ------------------------------------------------------------------ the MH kernel's logarithm and exponential
+// Table-driven (the scheme of the ARM optimized-routines / glibc 2.28+ `log` and `exp`, published algorithms; tables generated
+// by scripts/gen_tables.py into pwgs_tables.cuh and copied to shared memory by the kernel):
+//   x = 2^k z, z in [sqrt(2)/2, sqrt(2));  the top 7 bits of z's mantissa field pick (1/c, log c);  r = z/c - 1, |r| <= 2^-8;
+//   log x = (k ln2 + log c) + (r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6)).
+// 9 FP64 instructions per logarithm, no reciprocal and no division (the fdlibm form it replaces: 16 + one MUFU.RCP64H: the XU pipe
+// under the reciprocal seeds and int->fp64 conversions was a second limiter of the likelihood loop beside the FP64 pipe, see
+// scripts/micro/plain_round.cu), a dependency chain of 7 instead of 16.  Measured 2e-14 relative (pwgs_math_selftest), the
+// interval around z = 1 is exact in the table so arguments next to 1 keep their relative accuracy without a branch.
+// N independent evaluations are written step by step across the N values so that ptxas emits the chains interleaved.
+// NORMAL POSITIVE FINITE arguments only: the binomial means mu, 1 - mu (pwgs_create / pwgs_set_tree keep them inside (0, 1))
+// and the logsumexp sums in [1, 4].
+#define PWGS_LOG_TAB_COPIES 8            // interleaved copies of the logarithm table in shared memory, see pwgs_log_pos_n
+#define PWGS_LOG_TAB_DOUBLES (256 * PWGS_LOG_TAB_COPIES)
 
-// log(x) for NORMAL POSITIVE FINITE x only (no zero / negative / subnormal / inf / nan handling): the binomial means mu and
-// 1 - mu of the likelihood, which pwgs_create / pwgs_set_tree keep strictly inside (0, 1).  Same arithmetic as pwgs_log.
-__device__ __forceinline__ double pwgs_log_pos(double x)
+#define PWGS_EXP_TAB_DOUBLES 128
+// shared-memory image of the table: entry j of copy c at double2 index 8 j + c
+__device__ __forceinline__ void pwgs_log_tab_fill(double *dst, int tid, int nthreads)
 {
-    int hi = __double2hiint(x);
-    const int lo = __double2loint(x);
-    int e = (hi >> 20) - 1023;
-    hi &= 0x000fffff;
-    const int i = (hi + 0x95f64) & 0x100000;
-    hi |= i ^ 0x3ff00000;
-    e += i >> 20;
-    const double f = __hiloint2double(hi, lo) - 1.0;
-    const double d = 2.0 + f;
-    double y = pwgs_rcp_approx(d);
-    double t = fma(-d, y, 1.0);
-    y = fma(y, t, y);
-    t = fma(-d, y, 1.0);
-    y = fma(y, t, y);
-    double q = f * y;
-    q = fma(fma(-d, q, f), y, q);
-    const double z = q * q, w = z * z;
-    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
-                              6.666666666666735130e-01);
-    const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
-    return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(q, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+    for (int i = tid; i < 256 * PWGS_LOG_TAB_COPIES; i += nthreads) {
+        const int j = i / (2 * PWGS_LOG_TAB_COPIES), rest = i % (2 * PWGS_LOG_TAB_COPIES);      // rest = 2 c + {0: 1/c, 1: log c}
+        dst[i] = g_pwgs_log_tab[2 * j + (rest & 1)];
+    }
 }
-
-// N independent pwgs_log_pos evaluations written step by step across the N values, so that the instruction stream the
-// compiler emits alternates between the N dependency chains (it does not interleave N separate inlined calls on its own, and a
-// single chain leaves the FP64 pipe idle for most of its latency).
+// `tab`: the calling lane's copy, i.e. (const double2 *)table + (lane & 7)
 template <int N>
-__device__ __forceinline__ void pwgs_log_pos_n(const double (&x)[N], double (&r)[N])
+__device__ __forceinline__ void pwgs_log_pos_n(const double (&x)[N], double (&res)[N], const double2 *__restrict__ tab)
 {
-    // Few values stay live per chain (f, q, z, the Horner accumulator and the integer exponent) so that ptxas can keep all N
-    // chains interleaved inside the register budget: the polynomial is ONE Horner chain in z = s^2 (fdlibm splits it into even
-    // and odd halves for scalar ILP, which costs two more live doubles per chain; here the N chains are the ILP), the exponent
-    // is converted to fp64 only where it is used, and the tail needs nothing but f, s and the polynomial.
-    double f[N], d[N], y[N], t[N], q[N], z[N], R[N];
-    int k[N];
+    double r[N], w[N], r2[N], P[N];
 #pragma unroll
     for (int i = 0; i < N; i++) {
-        // x = 2^e * m with m in [sqrt(2)/2, sqrt(2)): shift the high word so that the exponent field changes exactly at sqrt(2)
-        const int hs = __double2hiint(x[i]) + (0x3ff00000 - 0x3fe6a09e);
-        k[i] = (hs >> 20) - 1023;
-        f[i] = __hiloint2double((hs & 0x000fffff) + 0x3fe6a09e, __double2loint(x[i])) - 1.0;
+        // hs: the high word moved down so that its exponent field IS k and changes exactly at sqrt(2) (0x3fe6a09e = high word
+        // of sqrt(2)/2); few integer instructions on purpose: the loop is close to issue-bound
+        const int hi = __double2hiint(x[i]);
+        const int hs = hi - 0x3fe6a09e;
+        const int k20 = hs & 0xfff00000;                                                             // k * 2^20
+        const double z = __hiloint2double(hi - k20, __double2loint(x[i]));
+        // interval j = (hs >> 13) & 127 lives at tab[8 j + (lane & 7)] (`tab` already points at the lane's copy): the 8 lanes of a
+        // quarter-warp then read 8 different 16-byte slots of the 128-byte rows, i.e. an LDS.128 is 4 conflict-free wavefronts
+        // whatever the 32 intervals are.  (One copy: 9.5 wavefronts per lookup with the 11 distinct means of a round, and the
+        // shared-memory pipe at 99 % was what bounded the loop: scripts/micro/plain_round.cu under ncu.)
+        const double2 t = *(const double2 *)((const char *)tab + ((hs & 0x000fe000) >> 6));
+        r[i] = fma(z, t.x, -1.0);
+        // k ln2 + log c in one rounding (the conversion takes k * 2^20 as it is, the constant is ln2 * 2^-20); |k| <= 1074 keeps
+        // the representation error of the single ln2 constant below 2.5e-14 absolute on |log| >= 0.69 |k|
+        w[i] = fma((double)k20, 6.931471805599453094e-01 / 1048576.0, t.y);
     }
 #pragma unroll
-    for (int i = 0; i < N; i++) d[i] = 2.0 + f[i];
+    for (int i = 0; i < N; i++) r2[i] = r[i] * r[i];
 #pragma unroll
-    for (int i = 0; i < N; i++) y[i] = pwgs_rcp_approx(d[i]);
-    // y ~ 1/d to 2^-20 from the hardware, 2^-40 after one Newton step, and s = f*y is used as it is: s only multiplies the
-    // O(f^2) part of log(1+f) = f - hf + s*(hf + R), so the logarithm comes out within 2e-13 relative (measured by
-    // pwgs_math_selftest) -- four orders of magnitude inside the 1e-9 the likelihood is specified to, at 20 FP64 instructions
-    // instead of the 24 a correctly rounded quotient costs.  K2 and pwgs_total_llh use the full-precision log().
+    for (int i = 0; i < N; i++) P[i] = fma(r[i], -1.0 / 6.0, 0.2);
 #pragma unroll
-    for (int i = 0; i < N; i++) t[i] = fma(-d[i], y[i], 1.0);
+    for (int i = 0; i < N; i++) P[i] = fma(r[i], P[i], -0.25);
 #pragma unroll
-    for (int i = 0; i < N; i++) y[i] = fma(y[i], t[i], y[i]);
+    for (int i = 0; i < N; i++) P[i] = fma(r[i], P[i], 1.0 / 3.0);
 #pragma unroll
-    for (int i = 0; i < N; i++) q[i] = f[i] * y[i];
+    for (int i = 0; i < N; i++) P[i] = fma(r[i], P[i], -0.5);
 #pragma unroll
-    for (int i = 0; i < N; i++) z[i] = q[i] * q[i];
-    // R = z*(Lg1 + z*(Lg2 + ... + z*Lg7))   (fdlibm e_log.c coefficients)
-#pragma unroll
-    for (int i = 0; i < N; i++) R[i] = fma(z[i], 1.479819860511658591e-01, 1.531383769920937332e-01);
-#pragma unroll
-    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 1.818357216161805012e-01);
-#pragma unroll
-    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 2.222219843214978396e-01);
-#pragma unroll
-    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 2.857142874366239149e-01);
-#pragma unroll
-    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 3.999999999940941908e-01);
-#pragma unroll
-    for (int i = 0; i < N; i++) R[i] = fma(z[i], R[i], 6.666666666666735130e-01);
-#pragma unroll
-    for (int i = 0; i < N; i++) R[i] = z[i] * R[i];
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        // log(1+f) = 2s + s*R and 2s = f - s*f  =>  log(1+f) = f - s*(f - R) (fdlibm's form for small exponents; its 0.5 f^2
-        // variant only buys the last ulp), then + k*ln2 in one fma: the hi/lo split of ln2 matters for huge |k| only; here
-        // |k| <= 1074 makes the representation error of the single constant at most 2.3e-14 absolute on |log| >= 0.69 |k|
-        const double u = fma(-q[i], f[i] - R[i], f[i]);
-        r[i] = fma((double)k[i], 6.931471805599453094e-01, u);
-    }
+    for (int i = 0; i < N; i++) res[i] = w[i] + fma(r2[i], P[i], r[i]);
 }
 template <int N>
 __device__ __forceinline__ void pwgs_div_pos_n(const double (&a)[N], const double (&b)[N], double (&r)[N])
@@ -219,33 +156,38 @@ __device__ __forceinline__ void pwgs_div_pos_n(const double (&a)[N], const doubl
 #pragma unroll
     for (int i = 0; i < N; i++) r[i] = a[i] * y[i];
 }
+// exp(x) for x <= 0 (arguments below -700 count as -700):  x = (128 k + i) ln2/128 + r, |r| <= ln2/256;
+// exp x = 2^k 2^(i/128) (1 + r + r^2 (1/2 + r/6 + r^2/24)): 10 FP64 instructions (the 13-term Horner form it replaces: 18);
+// 3e-15 relative (pwgs_math_selftest).
 template <int N>
-__device__ __forceinline__ void pwgs_exp_nonpos_n(const double (&xin)[N], double (&out)[N])
+__device__ __forceinline__ void pwgs_exp_nonpos_n(const double (&xin)[N], double (&out)[N], const double *__restrict__ tab)
 {
-    double x[N], kd[N], r[N], p[N];
-    int n[N];
+    double x[N], kd[N], r[N], r2[N], p[N], sc[N];
 #pragma unroll
     for (int i = 0; i < N; i++) x[i] = fmax(xin[i], -700.0);
 #pragma unroll
-    for (int i = 0; i < N; i++) kd[i] = fma(x[i], 1.4426950408889634074, 6755399441055744.0);
+    for (int i = 0; i < N; i++) kd[i] = fma(x[i], 1.8466496523378731e+02, 6755399441055744.0);      // 128/ln2; round to nearest integer
 #pragma unroll
-    for (int i = 0; i < N; i++) { n[i] = __double2loint(kd[i]); kd[i] -= 6755399441055744.0; }
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(kd[i], -6.93147180369123816490e-01, x[i]);
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = fma(kd[i], -1.90821492927058770002e-10, r[i]);
-    const double c[13] = {2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
-                          2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03,
-                          4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0};
-#pragma unroll
-    for (int i = 0; i < N; i++) p[i] = 1.6059043836821613e-10;
-#pragma unroll
-    for (int j = 0; j < 13; j++) {
-#pragma unroll
-        for (int i = 0; i < N; i++) p[i] = fma(p[i], r[i], c[j]);
+    for (int i = 0; i < N; i++) {
+        const int n = __double2loint(kd[i]);                                                        // 128 k + i  (<= 0)
+        kd[i] -= 6755399441055744.0;
+        const double t = tab[n & 127];
+        sc[i] = __hiloint2double(__double2hiint(t) + ((n >> 7) << 20), __double2loint(t));         // 2^k 2^(i/128): normal for x >= -700
     }
 #pragma unroll
-    for (int i = 0; i < N; i++) out[i] = __hiloint2double(__double2hiint(p[i]) + (n[i] << 20), __double2loint(p[i]));
+    for (int i = 0; i < N; i++) r[i] = fma(kd[i], -5.41521234663378e-03, x[i]);                     // ln2/128, high 32 bits: kd * hi is exact
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = fma(kd[i], -1.4907929134926466e-12, r[i]);                   // low part
+#pragma unroll
+    for (int i = 0; i < N; i++) r2[i] = r[i] * r[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(r[i], 1.0 / 24.0, 1.0 / 6.0);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(r[i], p[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < N; i++) p[i] = fma(r2[i], p[i], r[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) out[i] = fma(sc[i], p[i], sc[i]);
 }
 
 // log(w/4) and log(w) for state multiplicities w = 0..4 (index 0 unused)

@@ -361,9 +361,14 @@ __global__ void collapse_kernel(int Dp, int T, int C, const int *__restrict__ pa
 }
 
 // ============================================================================ K1
-#define MH_CWARPS 11                     // consumer warps (likelihood + bookkeeping); with the producer warp that is 12 warps = 3 per
-                                         // SM sub-partition, the most that fit at 168 registers (8 interleaved chains of fp64 logarithms per thread)
+// consumer warps (likelihood + bookkeeping); with the producer warp that is 12 warps = 3 per SM sub-partition at 168 registers.
+// Tried in round 2 and measured slower: a 13th warp (12 consumers + producer at 128 registers, the most a sub-partition with
+// four warps allows: 1.52 vs 1.43 ms, a warp's three groups take longer when four warps share a dispatch port), and full
+// batches cut into thirds of the data rounds so that 12 warps divide them evenly (1.69 ms: shares cost ~20 % more per datum).
+#define MH_CWARPS 11
+#define MH_MAXNREG 168
 #define MH_UNITS 32                      // work units (proposal group x share of the data rounds) a batch is cut into: ~3 per consumer warp
+#define MH_RED_DOUBLES(maxb) ((size_t)(maxb) > MH_BU * MH_UNITS ? (size_t)(maxb) : (size_t)MH_BU * MH_UNITS)
 #define MH_CONSUMERS (MH_CWARPS * 32)
 static_assert(PWGS_MAX_BATCH / 32 <= MH_CWARPS, "the publish / read-totals steps use one consumer thread per proposal");
 #define MH_THREADS (MH_CONSUMERS + 32)   // + one producer warp (proposal draws for the ring)
@@ -421,13 +426,13 @@ struct MhSmem {
     __device__ __forceinline__ double *lgsum(int e) const { return state0 + e * statestride + 4 * KT; }
     __device__ __forceinline__ double *slg(int e) const { return state0 + e * statestride + 4 * KT + T; }
     // two proposal buffers (current batch / next batch), `bufstride` doubles apart; the ring slots use the same layout
-    double *buf0;                                   // per buffer: pi1[MAXB*KT], phi1[MAXB*KT], hastings[MAXB*T], log r[MAXB]
+    double *buf0;                                   // per buffer: pi1, phi1 (groups of four proposals interleaved), hastings, log r: see mh_bufstride
     int bufstride, o_phi, o_hast, o_logr;
     __device__ __forceinline__ double *prop_pi(int b) const { return buf0 + b * bufstride; }
     __device__ __forceinline__ double *prop_phi(int b) const { return buf0 + b * bufstride + o_phi; }
     __device__ __forceinline__ double *hast(int b) const { return buf0 + b * bufstride + o_hast; }
     __device__ __forceinline__ double *logr(int b) const { return buf0 + b * bufstride + o_logr; }
-    double *red;                                    // [nb][warps per proposal group]: per-warp sums of the current batch
+    double *red;                                    // [nb][shares per proposal group]: per-share sums of the current batch
     double *llh;                                    // [MAXB]
     unsigned long long *seen;                       // [2][MAXB][2]: p.sums as of the last time this CTA read each parity
     double *pscratch;                               // [MH_CWARPS+1][2K] per warp: pi1 and phi1 of a proposal drawn for the ring
@@ -437,12 +442,24 @@ struct MhSmem {
 enum MhCtl { CTL_GEN = 0, CTL_DONE = 1, CTL_PROD_DONE = 2, CTL_ABORT = 3, CTL_JOB = 4 /* 2 x {state, it, nb} */, CTL_PRANGE = 12 /* MH_PCLASSES x {first, count} */,
              CTL_OK = 12 + 2 * MH_PCLASSES /* PWGS_MAX_BATCH / 32 ballots of the accept test */, CTL_WORDS = 12 + 2 * MH_PCLASSES + PWGS_MAX_BATCH / 32 };
 
-__host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return 2 * (size_t)maxb * K * T + (size_t)maxb * T + maxb; }
+// Proposal buffer (shared memory) = ring slot (global memory) layout, in doubles:
+//   pi1   [maxb][KT]                       proposal b, node/sample i at b*KT + i
+//   phi1  [ceil(maxb/4)][KT][4]            proposal b, node/sample i at mh_phi_at(b, i, KT): the four proposals a likelihood thread
+//                                          evaluates together are adjacent, so it reads them with two 16-byte loads
+//   hastings [maxb][T], log r [maxb]
+// Region offsets are even so that the phi region is 16-byte aligned.
+__host__ __device__ inline size_t mh_even(size_t x) { return (x + 1) & ~(size_t)1; }
+__host__ __device__ inline size_t mh_phi_doubles(int KT, int nb) { return (size_t)((nb + 3) & ~3) * KT; }
+__host__ __device__ inline size_t mh_o_phi(int KT, int maxb) { return mh_even((size_t)maxb * KT); }
+__host__ __device__ inline size_t mh_o_hast(int KT, int maxb) { return mh_o_phi(KT, maxb) + mh_phi_doubles(KT, maxb); }
+__host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return mh_even(mh_o_hast(K * T, maxb) + (size_t)maxb * T + maxb); }
+__host__ __device__ __forceinline__ int mh_phi_at(int b, int i, int KT) { return (b >> 2) * 4 * KT + i * 4 + (b & 3); }
 __host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
 {
     size_t KT = (size_t)K * T;
-    const size_t red = (size_t)maxb > MH_BU * MH_UNITS ? (size_t)maxb : MH_BU * MH_UNITS;
-    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 4 * (size_t)maxb + 2 * (size_t)K * (MH_CWARPS + 1);
+    const size_t red = MH_RED_DOUBLES(maxb);
+    return PWGS_LOG_TAB_DOUBLES + PWGS_EXP_TAB_DOUBLES + 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 4 * (size_t)maxb +
+           2 * (size_t)K * (MH_CWARPS + 1);
 }
 __host__ __device__ inline size_t mh_smem_ints(int K) { return CTL_WORDS + 2 * (size_t)K; }
 
@@ -460,8 +477,8 @@ __device__ __noinline__ double pwgs_lgamma(double x) { return lgamma(x); }
 // (mh.cpp:113-131, util.cpp:24-33), phi1 = subtree sums of pi1 (mh.cpp:134-141) and the Hastings correction of mh.cpp:80-93
 // for this sample; for tp == 0 also the log of the iteration's acceptance uniform (mh.cpp:95-96).  Lanes own the nodes
 // k = lane, lane+32, ...; every reduction is a fixed-shape shuffle tree, so all CTAs of a chain get bit-identical results.
-// x / ph: pi1 / phi1 of node k at [k * xs].
-__device__ __noinline__ void mh_propose(const MhParams &p, const MhSmem &S, int e, double *x, double *ph, int xs, double *hast_out,
+// x / ph: pi1 / phi1 of node k at x[k * xs] / ph[k * phs].
+__device__ __noinline__ void mh_propose(const MhParams &p, const MhSmem &S, int e, double *x, double *ph, int xs, int phs, double *hast_out,
                                         double *logr_out, int tp, uint32_t it, int lane)
 {
     const int T = p.T, K = p.K;
@@ -504,7 +521,7 @@ __device__ __noinline__ void mh_propose(const MhParams &p, const MhSmem &S, int 
             double v = x[j * xs];
             if (lo <= S.tin[j] && S.tout[j] <= hi) acc += v;
         }
-        if (real) ph[k * xs] = acc;
+        if (real) ph[k * phs] = acc;
         const double pn = real ? x[kk * xs] : 1.0, pv = cpi[kk * T + tp];
         const double lg = pwgs_lgamma(real ? mstd * pn : sa1), lpn = log(pn);
         if (real) {
@@ -533,7 +550,7 @@ __device__ __forceinline__ void mh_draw_local(const MhParams &p, const MhSmem &S
 #pragma unroll 1
     for (int task = warp; task < nb * T; task += MH_CWARPS) {
         const int b = task / T, tp = task - b * T;
-        mh_propose(p, S, e, S.prop_pi(buf) + b * KT + tp, S.prop_phi(buf) + b * KT + tp, T, S.hast(buf) + b * T + tp,
+        mh_propose(p, S, e, S.prop_pi(buf) + b * KT + tp, S.prop_phi(buf) + mh_phi_at(b, tp, KT), T, 4 * T, S.hast(buf) + b * T + tp,
                    S.logr(buf) + b, tp, (uint32_t)(it_first + b), lane);
     }
 }
@@ -590,6 +607,7 @@ struct SliceShared {
     __device__ __forceinline__ int cd(int tp, int i) const { return ((const int *)mh_sm)[o_cint + (1 + T + tp) * cstride + i]; }
     __device__ __forceinline__ int cenode(int e, int i) const { return ((const int *)mh_sm)[o_cint + (1 + 2 * T + e) * cstride + i]; }
     __device__ __forceinline__ int cecoef(int e, int i, int u) const { return ((const int *)mh_sm)[4 * (o_ecoef + e * cstride + i) + u]; }
+    __device__ __forceinline__ int4 cecoef4(int e, int i) const { return ((const int4 *)mh_sm)[o_ecoef + e * cstride + i]; }
 };
 struct SliceGlobal {
     int np, pstride, nc, cstride;
@@ -608,6 +626,7 @@ struct SliceGlobal {
     __device__ __forceinline__ int cd(int tp, int i) const { return __ldg(g_cd + (size_t)tp * cstride + i); }
     __device__ __forceinline__ int cenode(int e, int i) const { return __ldg(g_cenode + (size_t)e * cstride + i); }
     __device__ __forceinline__ int cecoef(int e, int i, int u) const { return __ldg((const int *)(g_cecoef + (size_t)e * cstride + i) + u); }
+    __device__ __forceinline__ int4 cecoef4(int e, int i) const { return __ldg(g_cecoef + (size_t)e * cstride + i); }
 };
 
 __host__ __device__ inline size_t mh_align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -621,10 +640,78 @@ __host__ __device__ inline size_t mh_stage_bytes(int pchunk, int cchunk, int T, 
     return b;
 }
 
+// phi1 of the BU proposals of a thread's group at node/sample index n: they are adjacent in the proposal buffer (mh_phi_at)
+template <int BU>
+__device__ __forceinline__ void mh_load_phi(const double *bphi, int n, double (&ph)[BU])
+{
+    if constexpr (BU == 4) {
+        const double2 lo = *(const double2 *)(bphi + 4 * n), hi = *(const double2 *)(bphi + 4 * n + 2);
+        ph[0] = lo.x; ph[1] = lo.y; ph[2] = hi.x; ph[3] = hi.y;
+    } else {
+#pragma unroll
+        for (int bb = 0; bb < BU; bb++) ph[bb] = bphi[4 * n + bb];
+    }
+}
+
+// One merged genome state u of a CNV-affected SSM for the BU proposals (mh.hpp:95-101): nr, nv = sum over the sparse entries of
+// delta * phi1, mixture mean, the two logarithms.  nd[e]: node/sample index of entry e (0 beyond the SSM's entries), cu[e]: its
+// packed (dnr, dnv) coefficients for this state (0 beyond).  A state whose nr + nv is not positive counts log(1e-99) (mh.hpp:100):
+// the arithmetic runs unconditionally (garbage in, garbage out, nothing traps) and the warp patches those values afterwards,
+// which keeps the selects out of the path every other SSM takes.
+template <int BU, class Slice>
+__device__ __forceinline__ void mh_cnv_state(const Slice &sl, const double *bphi, const double2 *ltab, int idx, int ne, int T, int tp,
+                                             const int (&nd)[4], const int (&cu)[4], int u, double mu_r, double omr, double fa, double fb,
+                                             double lw, double tiny, double (&val)[BU])
+{
+    double nr[BU], nv[BU];
+#pragma unroll
+    for (int bb = 0; bb < BU; bb++) nr[bb] = nv[bb] = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const double dr = (double)(short)(cu[e] & 0xffff), dv = (double)(cu[e] >> 16);
+        double ph[BU];
+        mh_load_phi<BU>(bphi, nd[e], ph);
+#pragma unroll
+        for (int bb = 0; bb < BU; bb++) { nr[bb] = fma(ph[bb], dr, nr[bb]); nv[bb] = fma(ph[bb], dv, nv[bb]); }
+    }
+#pragma unroll 1
+    for (int e = 4; e < ne; e++) {                                              // SSMs in three or more CNVs
+        const int c = sl.cecoef(e, idx, u);
+        const double dr = (double)(short)(c & 0xffff), dv = (double)(c >> 16);
+        double ph[BU];
+        mh_load_phi<BU>(bphi, sl.cenode(e, idx) * T + tp, ph);
+#pragma unroll
+        for (int bb = 0; bb < BU; bb++) { nr[bb] = fma(ph[bb], dr, nr[bb]); nv[bb] = fma(ph[bb], dv, nv[bb]); }
+    }
+    double num[BU], den[BU], mu[BU];
+    bool bad = false;
+#pragma unroll
+    for (int bb = 0; bb < BU; bb++) {
+        den[bb] = nr[bb] + nv[bb];
+        num[bb] = fma(nv[bb], omr, nr[bb] * mu_r);
+        bad |= !(den[bb] > 0.0);
+    }
+    pwgs_div_pos_n<BU>(num, den, mu);                                            // mh.hpp:96
+    double xx[2 * BU], ll[2 * BU];
+#pragma unroll
+    for (int bb = 0; bb < BU; bb++) { xx[bb] = mu[bb]; xx[BU + bb] = 1.0 - mu[bb]; }
+    pwgs_log_pos_n<2 * BU>(xx, ll, ltab);
+#pragma unroll
+    for (int bb = 0; bb < BU; bb++) val[bb] = fma(fa, ll[bb], fma(fb, ll[BU + bb], lw));
+    if (__any_sync(PWGS_FULL_MASK, bad)) {
+#pragma unroll
+        for (int bb = 0; bb < BU; bb++) val[bb] = den[bb] > 0.0 ? val[bb] : tiny;
+    }
+}
+
 // Likelihood of this CTA's slice of the data for the nb proposals of the batch (param_post, mh.cpp:153-166).  The consumer
 // warps are split into nb/BU groups; group g evaluates proposals g*BU .. g*BU+BU-1, each thread walking the CTA's data with
 // the group's stride and accumulating BU sums, so that every load / int->fp64 conversion is shared by BU proposals and the BU
 // independent chains of logarithms overlap in the FP64 pipe.  Leaves red[bb][warp] = the warp's sum for proposal g*BU+bb.
+// What bounds these loops is the warp scheduler's dispatch port: an FP64 instruction holds it for two cycles, any other
+// instruction for one (scripts/micro/plain_round.cu: time per round = 2 F + O at every occupancy), so beside the FP64 count the
+// number of address / select / move instructions around it decides the speed -- hence the 16-byte phi loads, the states peeled
+// out of their loop (no selects on the first one, no register shuffling between them) and the warp-level patch for nr + nv <= 0.
 template <int BU, class Slice>
 __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S, const Slice &sl, int cur, int wpg, int role, int g, int pcls,
                                               int lane, int rank, int cpc)
@@ -632,7 +719,9 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
     // proposal group g (proposals g*BU .. g*BU+BU-1) is evaluated by wpg warps; this warp is number `role` of them
     const int T = p.T, KT = p.K * T;
     const int tpg = wpg * 32, lt = role * 32 + lane;
-    const double *bphi = S.prop_phi(cur) + (g * BU) * KT;
+    const double2 *ltab = (const double2 *)mh_sm + (lane & (PWGS_LOG_TAB_COPIES - 1));   // tables of the logarithm (this lane's copy) and the
+    const double *etab = mh_sm + PWGS_LOG_TAB_DOUBLES;                  // exponential: first thing in the dynamic shared array
+    const double *bphi = S.prop_phi(cur) + mh_phi_at(g * BU, 0, KT);    // BU == 1: proposal g of its group of four, stride 4
     double acc[BU];
 #pragma unroll
     for (int bb = 0; bb < BU; bb++) acc[bb] = 0.0;
@@ -643,101 +732,75 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
     for (int l = lt; l - lane < cnt; l += tpg) {
         const bool act = l < cnt;
         const int idx = act ? l : 0;
-        const int code = act ? sl.ccode(idx) : 0;
-        const int ne = code & 0xff, nu = (code >> 8) & 3;
+        const int code = act ? sl.ccode(idx) : 0;                                // lanes past the end: no entries, no states (the
+        const int ne = code & 0xff, nu = (code >> 8) & 3;                        // round costs what its real SSMs cost)
         const int numax = __reduce_max_sync(PWGS_FULL_MASK, nu);
+        const double actd = act ? 1.0 : 0.0;                                     // lanes past the end of the list add nothing
         const double mu_r = sl.cmu_r(idx), omr = 1.0 - mu_r;
+        int nd0[4];
+        int4 cq[4];                                                              // entry e: packed coefficients of its (up to) 4 states
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const bool v = e < ne;
+            nd0[e] = v ? sl.cenode(e, idx) * T : 0;
+            cq[e] = v ? sl.cecoef4(e, idx) : make_int4(0, 0, 0, 0);
+        }
 #pragma unroll 1
         for (int tp = 0; tp < T; tp++) {
             const int a = sl.ca(tp, idx), d = sl.cd(tp, idx);
             const double lbc = sl.clbc(tp, idx), fa = (double)a, fb = (double)(d - a);
-            // states one after the other with a running (max, sum) pair: util.cpp:35-43 over the merged states
-            double mx[BU], sm[BU];
-#pragma unroll 1
-            for (int u = 0; u < numax; u++) {                                    // warp-uniform trip count
-                double nr[BU], nv[BU];
+            int nd[4];
 #pragma unroll
-                for (int bb = 0; bb < BU; bb++) nr[bb] = nv[bb] = 0.0;
-                // the first four entries are loaded up front (predicated) so their shared-memory latencies overlap; SSMs with
-                // more entries (three or more CNV links) finish in the loop below
-                {
-                    int nd[4], cu[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const bool v = e < ne;
-                        nd[e] = v ? sl.cenode(e, idx) * T + tp : 0;
-                        cu[e] = v ? sl.cecoef(e, idx, u) : 0;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const double dr = (double)(short)(cu[e] & 0xffff), dv = (double)(cu[e] >> 16);
-#pragma unroll
-                        for (int bb = 0; bb < BU; bb++) {
-                            const double ph = bphi[bb * KT + nd[e]];
-                            nr[bb] = fma(ph, dr, nr[bb]);
-                            nv[bb] = fma(ph, dv, nv[bb]);
-                        }
-                    }
-                }
-#pragma unroll 1
-                for (int e = 4; e < ne; e++) {
-                    const int node = sl.cenode(e, idx) * T + tp;
-                    const int cu = sl.cecoef(e, idx, u);
-                    const double dr = (double)(short)(cu & 0xffff), dv = (double)(cu >> 16);
-#pragma unroll
-                    for (int bb = 0; bb < BU; bb++) {
-                        const double ph = bphi[bb * KT + node];
-                        nr[bb] = fma(ph, dr, nr[bb]);
-                        nv[bb] = fma(ph, dv, nv[bb]);
-                    }
-                }
-                const int w = (code >> (12 + 4 * u)) & 7;
-                const double lw = lbc + c_logw4[w], tiny = p.log_tiny + c_logw[w];
-                double num[BU], den[BU], mu[BU], om[BU];
-#pragma unroll
-                for (int bb = 0; bb < BU; bb++) {
-                    den[bb] = nr[bb] + nv[bb];
-                    num[bb] = fma(nv[bb], omr, nr[bb] * mu_r);
-                }
-                pwgs_div_pos_n<BU>(num, den, mu);                                                              // mh.hpp:96
-#pragma unroll
-                for (int bb = 0; bb < BU; bb++) { mu[bb] = den[bb] > 0.0 ? mu[bb] : 0.5; om[bb] = 1.0 - mu[bb]; }
-                double xx[2 * BU], ll[2 * BU];
-#pragma unroll
-                for (int bb = 0; bb < BU; bb++) { xx[bb] = mu[bb]; xx[BU + bb] = om[bb]; }
-                pwgs_log_pos_n<2 * BU>(xx, ll);
-                double val[BU];
-#pragma unroll
-                for (int bb = 0; bb < BU; bb++) {
-                    val[bb] = fma(fa, ll[bb], fma(fb, ll[BU + bb], lw));
-                    val[bb] = u < nu ? (den[bb] > 0.0 ? val[bb] : tiny) : -INFINITY;                           // mh.hpp:95-101
-                }
-                if (u == 0) {
-#pragma unroll
-                    for (int bb = 0; bb < BU; bb++) { mx[bb] = val[bb]; sm[bb] = 1.0; }
-                } else {
-                    // running logsumexp: of exp(mx - nm) and exp(val - nm) one is exp(0) = 1, so one exponential does
-                    double xe[BU], ee[BU];
-#pragma unroll
-                    for (int bb = 0; bb < BU; bb++) xe[bb] = -fabs(mx[bb] - val[bb]);
-                    pwgs_exp_nonpos_n<BU>(xe, ee);
-#pragma unroll
-                    for (int bb = 0; bb < BU; bb++) {
-                        const bool up = val[bb] > mx[bb];
-                        sm[bb] = fma(sm[bb], up ? ee[bb] : 1.0, up ? 1.0 : ee[bb]);
-                        mx[bb] = up ? val[bb] : mx[bb];
-                    }
-                }
+            for (int e = 0; e < 4; e++) nd[e] = nd0[e] + tp;
+            // states one after the other: util.cpp:35-43 over the merged states, weights folded into the terms
+            double v0[BU];
+            {
+                const int w = (code >> 12) & 7;
+                const int cu[4] = {cq[0].x, cq[1].x, cq[2].x, cq[3].x};
+                mh_cnv_state<BU>(sl, bphi, ltab, idx, ne, T, tp, nd, cu, 0, mu_r, omr, fa, fb, lbc + c_logw4[w], p.log_tiny + c_logw[w], v0);
             }
             if (numax <= 1) {
 #pragma unroll
-                for (int bb = 0; bb < BU; bb++) acc[bb] += act ? mx[bb] : 0.0;
-            } else {
-                double ls[BU];
-                pwgs_log_pos_n<BU>(sm, ls);
-#pragma unroll
-                for (int bb = 0; bb < BU; bb++) acc[bb] += act ? mx[bb] + ls[bb] : 0.0;
+                for (int bb = 0; bb < BU; bb++) acc[bb] = fma(actd, v0[bb], acc[bb]);
+                continue;
             }
+            double mx[BU], sm[BU];
+            {
+                double v1[BU], xe[BU], ee[BU];
+                const int w = (code >> 16) & 7;
+                const int cu[4] = {cq[0].y, cq[1].y, cq[2].y, cq[3].y};
+                mh_cnv_state<BU>(sl, bphi, ltab, idx, ne, T, tp, nd, cu, 1, mu_r, omr, fa, fb, lbc + c_logw4[w], p.log_tiny + c_logw[w], v1);
+                // logsumexp of two: max + log(1 + exp(-|difference|)); an SSM with a single state contributes exp(-inf) = 0
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) {
+                    v1[bb] = 1 < nu ? v1[bb] : -INFINITY;
+                    mx[bb] = fmax(v0[bb], v1[bb]);
+                    xe[bb] = -fabs(v0[bb] - v1[bb]);
+                }
+                pwgs_exp_nonpos_n<BU>(xe, ee, etab);
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) sm[bb] = 1.0 + ee[bb];
+            }
+            if (numax > 2) {
+                double v2[BU], xe[BU], ee[BU];
+                const int w = (code >> 20) & 7;
+                const int cu[4] = {cq[0].z, cq[1].z, cq[2].z, cq[3].z};
+                mh_cnv_state<BU>(sl, bphi, ltab, idx, ne, T, tp, nd, cu, 2, mu_r, omr, fa, fb, lbc + c_logw4[w], p.log_tiny + c_logw[w], v2);
+                // running (max, sum): of exp(mx - nm) and exp(v2 - nm) one is exp(0) = 1, so one exponential does
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) { v2[bb] = 2 < nu ? v2[bb] : -INFINITY; xe[bb] = -fabs(mx[bb] - v2[bb]); }
+                pwgs_exp_nonpos_n<BU>(xe, ee, etab);
+#pragma unroll
+                for (int bb = 0; bb < BU; bb++) {
+                    const bool up = v2[bb] > mx[bb];
+                    sm[bb] = fma(sm[bb], up ? ee[bb] : 1.0, up ? 1.0 : ee[bb]);
+                    mx[bb] = up ? v2[bb] : mx[bb];
+                }
+            }
+            double ls[BU];
+            pwgs_log_pos_n<BU>(sm, ls, ltab);
+#pragma unroll
+            for (int bb = 0; bb < BU; bb++) acc[bb] = fma(actd, mx[bb] + ls[bb], acc[bb]);
         }
     }
 
@@ -753,14 +816,14 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
         for (int tp = 0; tp < T; tp++) {
             const int a = sl.pa(tp, jj), d = sl.pd(tp, jj);
             const double fa = act ? (double)a : 0.0, fb = act ? (double)(d - a) : 0.0;
-            double xx[2 * BU], ll[2 * BU];
+            double xx[2 * BU], ll[2 * BU], ph[BU];
+            mh_load_phi<BU>(bphi, nodeT + tp, ph);
 #pragma unroll
             for (int bb = 0; bb < BU; bb++) {
-                const double phi = bphi[bb * KT + nodeT + tp];
-                xx[bb] = fma(phi, dmu, mu_r);                       // (1-phi)*mu_r + phi*mu_v (mh.hpp:87) in one rounding
+                xx[bb] = fma(ph[bb], dmu, mu_r);                    // (1-phi)*mu_r + phi*mu_v (mh.hpp:87) in one rounding
                 xx[BU + bb] = 1.0 - xx[bb];
             }
-            pwgs_log_pos_n<2 * BU>(xx, ll);
+            pwgs_log_pos_n<2 * BU>(xx, ll, ltab);
 #pragma unroll
             for (int bb = 0; bb < BU; bb++) acc[bb] = fma(fa, ll[bb], fma(fb, ll[BU + bb], acc[bb]));
         }
@@ -774,14 +837,14 @@ __device__ __forceinline__ void mh_likelihood(const MhParams &p, const MhSmem &S
             const int ee = act ? e : 0, k = ee / (C * T), c = (ee / T) % C, tp = ee % T;
             const double A = act ? (double)p.cl_sums[2 * ee] : 0.0, B = act ? (double)p.cl_sums[2 * ee + 1] : 0.0;
             const double mu_r = p.cl_mu_r[c], dmu = p.cl_mu_v[c] - mu_r;
-            double xx[2 * BU], ll[2 * BU];
+            double xx[2 * BU], ll[2 * BU], ph[BU];
+            mh_load_phi<BU>(bphi, k * T + tp, ph);
 #pragma unroll
             for (int bb = 0; bb < BU; bb++) {
-                const double phi = bphi[bb * KT + k * T + tp];
-                xx[bb] = fma(phi, dmu, mu_r);
+                xx[bb] = fma(ph[bb], dmu, mu_r);
                 xx[BU + bb] = 1.0 - xx[bb];
             }
-            pwgs_log_pos_n<2 * BU>(xx, ll);
+            pwgs_log_pos_n<2 * BU>(xx, ll, ltab);
 #pragma unroll
             for (int bb = 0; bb < BU; bb++) acc[bb] = fma(A, ll[bb], fma(B, ll[BU + bb], acc[bb]));
         }
@@ -800,12 +863,12 @@ __device__ __forceinline__ void mh_draw_to_slot(const MhParams &p, const MhSmem 
     const int T = p.T, K = p.K, KT = K * T;
     double *x = S.pscratch + (size_t)scratch * 2 * K;
     double hast = 0.0, logr = 0.0;
-    mh_propose(p, S, e, x, x + K, 1, &hast, &logr, tp, it, lane);
+    mh_propose(p, S, e, x, x + K, 1, 1, &hast, &logr, tp, it, lane);
     __syncwarp();
 #pragma unroll 1
     for (int k = lane; k < K; k += 32) {
         slot[(size_t)b * KT + k * T + tp] = x[k];
-        slot[(size_t)S.o_phi + (size_t)b * KT + k * T + tp] = x[K + k];
+        slot[(size_t)S.o_phi + mh_phi_at(b, k * T + tp, KT)] = x[K + k];
     }
     if (lane == 0) {
         slot[(size_t)S.o_hast + b * T + tp] = hast;
@@ -883,7 +946,8 @@ __device__ __noinline__ bool mh_epoch_start(const MhParams &p, const MhSmem &S, 
     consumer_sync();
     if (S.ctl[CTL_ABORT]) return true;
     double *dst = S.prop_pi(buf);
-    for (int i = tid; i < n0 * KT; i += MH_CONSUMERS) { dst[i] = __ldcg(es0 + i); dst[S.o_phi + i] = __ldcg(es0 + S.o_phi + i); }
+    for (int i = tid; i < n0 * KT; i += MH_CONSUMERS) dst[i] = __ldcg(es0 + i);
+    for (int i = tid; i < (int)mh_phi_doubles(KT, n0); i += MH_CONSUMERS) dst[S.o_phi + i] = __ldcg(es0 + S.o_phi + i);
     for (int i = tid; i < n0 * T; i += MH_CONSUMERS) dst[S.o_hast + i] = __ldcg(es0 + S.o_hast + i);
     for (int i = tid; i < n0; i += MH_CONSUMERS) dst[S.o_logr + i] = __ldcg(es0 + S.o_logr + i);
     return false;
@@ -902,7 +966,7 @@ __device__ __noinline__ bool mh_epoch_start(const MhParams &p, const MhSmem &S, 
 // batch by the producer warp of its owner CTA two batches ahead (mh_ring_tasks) -- and travels through a ring in global memory
 // under the chain barrier's release / acquire.  Chains with few CTAs draw locally in every CTA.
 template <bool STAGED>
-__global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, int cpc)
+__global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ plist, int cpc)
 {
     double *sm = mh_sm;
     __shared__ MhParams p;                              // this chain's descriptor (grid = n_chains * cpc CTAs)
@@ -915,21 +979,23 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
 
     MhSmem S;
     {
-        double *q = sm;
+        double *q = sm + PWGS_LOG_TAB_DOUBLES + PWGS_EXP_TAB_DOUBLES;
         S.KT = KT; S.T = T; S.statestride = 4 * KT + 2 * T;
         S.state0 = q; q += 2 * S.statestride;
-        S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = MAXB * KT; S.o_hast = 2 * MAXB * KT; S.o_logr = 2 * MAXB * KT + MAXB * T;
+        S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = (int)mh_o_phi(KT, MAXB); S.o_hast = (int)mh_o_hast(KT, MAXB); S.o_logr = S.o_hast + MAXB * T;
         S.buf0 = q; q += 2 * S.bufstride;
-        S.red = q; q += (MAXB > MH_BU * MH_UNITS ? MAXB : MH_BU * MH_UNITS); S.llh = q; q += MAXB;
+        S.red = q; q += MH_RED_DOUBLES(MAXB); S.llh = q; q += MAXB;
         S.seen = (unsigned long long *)q; q += 4 * MAXB;
         S.pscratch = q; q += 2 * K * (MH_CWARPS + 1);
         S.ctl = (volatile int *)q; S.tin = (int *)q + CTL_WORDS; S.tout = S.tin + K;
     }
+    pwgs_log_tab_fill(sm, tid, MH_THREADS);
+    for (int i = tid; i < PWGS_EXP_TAB_DOUBLES; i += MH_THREADS) sm[PWGS_LOG_TAB_DOUBLES + i] = g_pwgs_exp_tab[i];
     for (int i = tid; i < KT; i += MH_THREADS) {
         S.pi(0)[i] = p.pi0[i];
         S.phi(0)[i] = p.phi0[i];
         S.prop_pi(0)[i] = p.pi0[i];                    // slot 0 of buffer 0 carries the entry state through the first pass
-        S.prop_phi(0)[i] = p.phi0[i];
+        S.prop_phi(0)[mh_phi_at(0, i, KT)] = p.phi0[i];
     }
     for (int k = tid; k < K; k += MH_THREADS) { S.tin[k] = p.tin[k]; S.tout[k] = p.tout[k]; }
     if (tid < CTL_PRANGE) S.ctl[tid] = 0;             // (the CTL_PRANGE words are written below)
@@ -1035,6 +1101,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
             // smaller batches: every group is cut into wpg shares of the data rounds (share r walks rounds r, r+wpg, ...) so that
             // there are MH_UNITS units of work again, dealt to the warps in turn like the groups of a full batch.  A group's
             // class (which partition of the plain data it walks) depends on the group alone, so its shares tile the list.
+            // (Shares cost ~20 % more per datum than whole groups -- per-unit set-up and reductions -- so full batches do not use them.)
             const int gfull = max(1, MAXB / MH_BU);
 #pragma unroll 1
             for (int v = warp; v < MH_UNITS; v += MH_CWARPS) {
@@ -1108,8 +1175,10 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         const bool fetch = !next_local && n1_nb > 0;
         const double *slot = p.ring + (size_t)(j == 0 ? MH_RING + 1 : (g + 1) % MH_RING) * (size_t)S.bufstride;   // epoch slot 1 / ring
         double f_pi = 0.0, f_phi = 0.0, f_h = 0.0, f_r = 0.0;
+        const int n1_phi = (int)mh_phi_doubles(KT, n1_nb);
         if (fetch) {
-            if (tid < n1_nb * KT) { f_pi = __ldcg(slot + tid); f_phi = __ldcg(slot + S.o_phi + tid); }
+            if (tid < n1_nb * KT) f_pi = __ldcg(slot + tid);
+            if (tid < n1_phi) f_phi = __ldcg(slot + S.o_phi + tid);
             if (tid < n1_nb * T) f_h = __ldcg(slot + S.o_hast + tid);
             if (tid < n1_nb) f_r = __ldcg(slot + S.o_logr + tid);
         }
@@ -1135,10 +1204,12 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         }
         if (fetch) {
             double *dst = S.prop_pi(cur ^ 1);
-            if (tid < n1_nb * KT) { dst[tid] = f_pi; dst[S.o_phi + tid] = f_phi; }
+            if (tid < n1_nb * KT) dst[tid] = f_pi;
+            if (tid < n1_phi) dst[S.o_phi + tid] = f_phi;
             if (tid < n1_nb * T) dst[S.o_hast + tid] = f_h;
             if (tid < n1_nb) dst[S.o_logr + tid] = f_r;
-            for (int i = tid + MH_CONSUMERS; i < n1_nb * KT; i += MH_CONSUMERS) { dst[i] = __ldcg(slot + i); dst[S.o_phi + i] = __ldcg(slot + S.o_phi + i); }
+            for (int i = tid + MH_CONSUMERS; i < n1_nb * KT; i += MH_CONSUMERS) dst[i] = __ldcg(slot + i);
+            for (int i = tid + MH_CONSUMERS; i < n1_phi; i += MH_CONSUMERS) dst[S.o_phi + i] = __ldcg(slot + S.o_phi + i);
             for (int i = tid + MH_CONSUMERS; i < n1_nb * T; i += MH_CONSUMERS) dst[S.o_hast + i] = __ldcg(slot + S.o_hast + i);
         }
         consumer_sync();
@@ -1166,7 +1237,7 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
         cur_llh = S.llh[sel];
         for (int i = tid; i < KT; i += MH_CONSUMERS) {
             S.pi(e ^ 1)[i] = S.prop_pi(cur)[sel * KT + i];
-            S.phi(e ^ 1)[i] = S.prop_phi(cur)[sel * KT + i];
+            S.phi(e ^ 1)[i] = S.prop_phi(cur)[mh_phi_at(sel, i, KT)];
         }
         accepted++;
         e ^= 1;
@@ -1208,13 +1279,17 @@ __global__ void __maxnreg__(168) mh_kernel(const MhParams *__restrict__ plist, i
 // through pwgs_div_pos_n; four values per thread, like the kernel uses them.
 __global__ void math_selftest_kernel(int n, const double *__restrict__ x, double *__restrict__ out)
 {
+    __shared__ __align__(16) double tabs[PWGS_LOG_TAB_DOUBLES + PWGS_EXP_TAB_DOUBLES];
+    pwgs_log_tab_fill(tabs, threadIdx.x, blockDim.x);
+    for (int t = threadIdx.x; t < PWGS_EXP_TAB_DOUBLES; t += blockDim.x) tabs[PWGS_LOG_TAB_DOUBLES + t] = g_pwgs_exp_tab[t];
+    __syncthreads();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
     double v[4], l[4], e[4], nx[4], den[4], q[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) { v[k] = x[min(i + k, n - 1)]; nx[k] = -v[k]; den[k] = 1.0 + v[k]; }
-    pwgs_log_pos_n<4>(v, l);
-    pwgs_exp_nonpos_n<4>(nx, e);
+    pwgs_log_pos_n<4>(v, l, (const double2 *)tabs + (threadIdx.x & (PWGS_LOG_TAB_COPIES - 1)));
+    pwgs_exp_nonpos_n<4>(nx, e, tabs + PWGS_LOG_TAB_DOUBLES);
     pwgs_div_pos_n<4>(v, den, q);
 #pragma unroll
     for (int k = 0; k < 4; k++)

@@ -14,7 +14,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "config3"
 s, _ = bench.workload(name)
 eng = P.Engine(device=0, **synth.data_kwargs(s))
 eng.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
-if len(sys.argv) > 2:
+if len(sys.argv) > 2 and sys.argv[2] != "-v":
     for n, v in zip(("mh_w_plain", "mh_w_cnv1", "mh_w_cnv2", "mh_w_cnv3"), sys.argv[2].split(",")):
         eng.set_option(n, int(v))
 eng.set_option("mh_profile", 1)
@@ -37,3 +37,6 @@ if "-v" in sys.argv:
     for k in sorted(set(map(tuple, X.tolist()))):
         sel = np.all(X == np.array(k), axis=1)
         print("rounds (plain, cnv1, cnv2, cnv3) = (%.2f, %d, %d, %d): %3d CTAs, cycles min %.0f mean %.0f max %.0f" % (k + (sel.sum(), cyc[sel].min(), cyc[sel].mean(), cyc[sel].max())))
+    order = np.argsort(-cyc)[:4]
+    for r_ in order:
+        print("slowest CTAs: rank %d cycles %.0f rounds %s" % (r_, cyc[r_], X[r_].tolist()))
