@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — MH iterations/s of the PhyloWGS hot path on B200 (metric of BASELINE.json).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config3|config4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config1|config2|config3|config4|config5:<n_ssm>[:<T>[:nocnv]]]
 
 One "step" = one `params.metropolis()`-sized pass of the hot path: MH_ITR = 5000 Metropolis-Hastings iterations
 (evolve.py:318 default) over the synthetic WGS tumour of BASELINE.json configs[2] (50k SSMs, 300 CNVs, 8 true
@@ -42,22 +42,40 @@ MH_STD = 100.0         # evolve.py:387
 METRIC = "mh_iterations_per_s"
 UNIT = "it/s"
 
-# FP64-pipe instruction model of ONE proposal-likelihood pass, counted from this repo's sm_100a code (DESIGN.md "Roofline";
-# DFMA/DADD/DMUL/DSETP/DMNMX thread-instructions; conversions and MUFU run on other pipes):
-FP64_LOG = 16                     # pwgs_log_pos_n: 2 DADD, reciprocal 2, quotient 1, z 1, Horner polynomial 7, tail 3
-FP64_PLAIN_TERM = 2 + 2 * FP64_LOG + 2                     # mu (one fma), 1-mu ; two logs ; two fmas into the sum           = 36
-FP64_CNV_STATE = 10 + 2 * FP64_LOG                         # nr+nv, mixture mean (division = 3), select, two logs, combine = 42
+# FP64-pipe instruction model of ONE proposal-likelihood pass (DFMA/DADD/DMUL/DSETP/DMNMX thread-instructions; conversions and
+# MUFU run on the XU pipe), read off the cubin: profiles/r02_mh_kernel_sass_histogram.txt (scripts/sass_histogram.py) lists the
+# loops of mh_kernel<true> with their opcode counts -- the plain loop has 88 FP64 instructions per round of 4 proposals (22 per
+# term), the CNV state body 28 per proposal beside its two DFMAs per entry.  (Round 1's fdlibm-style logarithm: 16 per log, 36
+# per plain term.)
+FP64_LOG = 9                      # pwgs_log_pos_n (table-driven): r, k ln2 + log c, r^2, four Horner steps, r + r^2 P, final add
+FP64_EXP = 10                     # pwgs_exp_nonpos_n: clamp, k, k - magic, two-part reduction, r^2, three polynomial steps, scale
+FP64_PLAIN_TERM = 2 + 2 * FP64_LOG + 2                     # mu (one fma), 1-mu ; two logs ; two fmas into the sum           = 22
+FP64_CNV_STATE = 10 + 2 * FP64_LOG                         # nr+nv, mixture mean (3 + division 3), test, 1-mu, two logs, combine = 28
 FP64_CNV_PER_ENTRY = 2                                     # two DFMAs per sparse (node, state) entry
-FP64_LSE_EXTRA_STATE = 24                                  # running logsumexp: difference, ONE exp (19), selects, fma
+FP64_LSE_EXTRA_STATE = 4 + FP64_EXP                        # logsumexp: max, difference, ONE exp, 1 + e (or the running-sum fma) = 14
 FP64_LSE_FINAL = FP64_LOG + 1                              # log of the sum (only when an SSM has more than one merged state)
 
 
 def workload(name):
+    """-> (dict of arrays: data + the fixed tree / assignment of the bench state, description)."""
     from phylowgs_b200 import synth
     if name == "config3":
         return synth.config(3), "synthetic WGS tumour: 50k SSMs, 300 CNVs, 8 true subclones, T=1 (BASELINE.json configs[2])"
     if name == "config4":
         return synth.config(4), "synthetic multi-region: 20k SSMs x 5 samples (BASELINE.json configs[3])"
+    if name == "config1":
+        return synth.from_files(os.path.join(ROOT, "tests", "golden", "ssm_data.txt"), os.path.join(ROOT, "tests", "golden", "cnv_data.txt"), 2), \
+            "the reference's bundled example: 11 SSMs + 1 CNV x 5 samples (BASELINE.json configs[0]), two-population chain tree"
+    if name == "config2":
+        return synth.from_files(os.path.join(ROOT, "tests", "golden", "emptysim.6.300.2000.ssm.txt"), None, 6), \
+            "phylowgs_sims emptysim.6.300.2000: 10k SSMs, no CNVs, T=1 (BASELINE.json configs[1]), six-population chain tree"
+    if name.startswith("config5"):                     # config5:<n_ssm>[:<T>[:nocnv]]  (BASELINE.json configs[4]: 1k-500k SSMs)
+        tok = name.split(":")
+        n = int(tok[1]) if len(tok) > 1 else 100000
+        T = int(tok[2]) if len(tok) > 2 else 1
+        nocnv = len(tok) > 3 and tok[3] == "nocnv"
+        s = synth.make_synthetic(n, 0 if nocnv else max(1, n * 3 // 500), T, 8, seed=1005, frac_cnv=0.0 if nocnv else 0.3, depth=60)
+        return s, "scaling sweep: %d SSMs, %s, T=%d (BASELINE.json configs[4])" % (n, "no CNVs" if nocnv else "30 %% of them in %d CNVs" % max(1, n * 3 // 500), T)
     raise SystemExit("unknown workload " + name)
 
 
@@ -165,9 +183,11 @@ def time_reference(s, chains, iters_sample, mh_std=MH_STD):
         def timed(iters):
             t0 = time.perf_counter()
             procs = []
+            cores = sorted(os.sched_getaffinity(0))
             for c in range(chains):
                 cmd, _ = run_mh_o(files, data, tree, iters, wd, tag=str(c), mh_std=mh_std)
-                procs.append(subprocess.Popen(cmd))
+                core = cores[c % len(cores)]                                # one core per chain (N chains = N x 1 core)
+                procs.append(subprocess.Popen(cmd, preexec_fn=lambda core=core: os.sched_setaffinity(0, {core})))
             for p in procs:
                 if p.wait() != 0:
                     raise SystemExit("reference mh.o failed")
@@ -286,6 +306,10 @@ def main():
                                                         "partition (default: the library's)")
     ap.add_argument("--cpu-sample-iters", type=int, default=400, help="MH iterations of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-accept-sweep", action="store_true")
+    ap.add_argument("--no-oracle-check", action="store_true")
+    ap.add_argument("--no-tree-samples", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="tuning: library option name=value (pwgs_set_option), repeatable")
     ap.add_argument("--mh-std", type=float, default=MH_STD, help="proposal concentration (evolve.py adapts it between 100 and 10000)")
     ap.add_argument("--profile-phases", action="store_true", help="print the MH kernel's per-phase cycle counters (CTA 0) to stderr")
     args = ap.parse_args()
@@ -299,7 +323,8 @@ def main():
     K = len(s["parent"])
     by_it, _, D, M, T = algorithmic_work(s, K)
     config = {"workload": wl_desc, "n_ssm": int(s["n_ssm"]), "n_cnv": int(D - s["n_ssm"]), "n_cnv_affected_ssm": M, "ntps": T,
-              "tree_nodes": K, "mh_iterations_per_step": MH_ITR, "mh_std": mh_std, "chains": n_gpus, "parallelism": "1 chain per GPU, no collective (timing barrier over gloo)"}
+              "tree_nodes": K, "mh_iterations_per_metropolis_call": MH_ITR, "mh_std": mh_std, "chains": n_gpus,
+              "parallelism": "1 chain per GPU, no collective (timing barrier over gloo)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -314,11 +339,12 @@ def main():
                 steps.append(r)
         rate = statistics.mean(x["rate"] for x in steps)
         ms = 1e3 * statistics.mean(x["t_run"] for x in steps)
-        sample = ("%d concurrent oracle/_ref/mh.o (unmodified mh.cpp+util.cpp, g++ -O3, GSL shim), MH_ITR=%d per step on the %s inputs; "
-                  "rate = MH_ITR/(t(MH_ITR)-t(0)), t(0)=%.2fs text re-parse per call excluded" % (n_gpus, args.cpu_sample_iters, args.workload, steps[-1]["t_parse"]))
+        sample = ("%d concurrent oracle/_ref/mh.o (unmodified mh.cpp+util.cpp, g++ -O3, GSL shim), each pinned to its own core, a bounded "
+                  "sample of MH_ITR=%d iterations per step on the %s inputs; rate = MH_ITR/(t(MH_ITR)-t(0)), t(0)=%.2fs text re-parse per "
+                  "call excluded" % (n_gpus, args.cpu_sample_iters, args.workload, steps[-1]["t_parse"]))
         line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config, "accept_ratio": acc,
+                "ms_per_step": ms, "mh_iterations_per_step": args.cpu_sample_iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "accept_ratio": acc,
                 "cpu_baseline": {"value": rate, "unit": UNIT, "cores": n_gpus, "kind": "reference", "sample": sample},
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -354,6 +380,9 @@ def main():
     if args.round_weights:
         for name, v in zip(("mh_w_plain", "mh_w_cnv1", "mh_w_cnv2", "mh_w_cnv3"), args.round_weights.split(",")):
             eng.set_option(name, int(v))
+    for kv in args.opt:
+        name, v = kv.split("=")
+        eng.set_option(name, int(v))
     if args.profile_phases:
         eng.set_option("mh_profile", 1)
     stats = [eng.get_option(n) for n in ("cnv_nu1", "cnv_nu2", "cnv_nu3", "cnv_entry_states")]
@@ -411,6 +440,49 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = n_gpus * args.steps * MH_ITR / e2e_s
 
+    # ---- once, outside the timed regions: the timed workload's result against the CPU oracle (1e-9 relative, north_star)
+    oracle_check = None
+    if rank == 0 and not args.no_oracle_check:
+        from oracle import oracle as O
+        od = O.Data(s["a"], s["d"], s["mu_r"], s["mu_v"], s["n_ssm"], s["cnv_ptr"], s["cnv_idx"], s["cnv_c1"], s["cnv_c2"])
+        ot = O.Tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
+        eng.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
+        res = eng.mh_run(MH_ITR, mh_std, seed, chain_stream(rank, 1, 0))         # the first timed launch again, outputs fetched
+        want_entry = O.multi_param_post(od, ot)
+        want_final = O.multi_param_post(od, ot, res["phi"], res["pi"])
+        got_entry = eng.total_llh(P.SEM_MH)
+        rel_entry = abs(got_entry - want_entry) / abs(want_entry)
+        rel_final = abs(res["llh"] - want_final) / abs(want_final)
+        oracle_check = {"entry_llh_rel_err": rel_entry, "final_llh_rel_err": rel_final, "accepted": int(round(res["ratio"] * MH_ITR)),
+                        "tolerance": 1e-9, "what": "pwgs_total_llh at the entry state and the timed launch's final log-likelihood against "
+                                                   "oracle multi_param_post (mh.cpp:147-166 restated, pinned to the compiled reference)"}
+        if not (rel_entry <= 1e-9 and rel_final <= 1e-9):
+            raise SystemExit("bench: the timed workload disagrees with the oracle: %r" % (oracle_check,))
+
+    # ---- the accept path: the same launches at proposal concentrations that make the chain accept (evolve.py:201-206 doubles
+    # mh_std up to 10 000 while fewer than 8 % are accepted); kernel time only, CPU beside it at the same mh_std
+    accept_sweep = None
+    if rank == 0 and world == 1 and not args.no_accept_sweep:
+        accept_sweep = []
+        for std in [x for x in (100.0, 1.0e4, 1.0e5, 1.0e6) if x != mh_std] + [mh_std]:
+            ks, rs = [], []
+            for k in range(3 + min(args.steps, 10)):
+                with torch.cuda.stream(ext):
+                    flush.zero_()
+                eng.mh_launch(MH_ITR, std, seed, chain_stream(rank, 4, k))
+                r = eng.mh_wait(fetch=False)
+                if k >= 3:
+                    ks.append(r["kernel_ms"])
+                    rs.append(r["ratio"])
+            its = MH_ITR / (statistics.mean(ks) * 1e-3)
+            row = {"mh_std": std, "value": its, "unit": UNIT, "kernel_ms_per_launch": statistics.mean(ks), "accept_ratio": statistics.mean(rs),
+                   "roofline_frac": fp_it * its / fp64_peak}
+            if not args.no_cpu_baseline:
+                rr = time_reference(s, 1, max(100, args.cpu_sample_iters // 2), std)
+                row["cpu_baseline"] = {"value": rr["rate"], "unit": UNIT, "cores": 1, "kind": "reference", "accept_ratio": rr["accept"]}
+            accept_sweep.append(row)
+        accept_sweep.sort(key=lambda r: r["mh_std"])
+
     if args.profile_phases and rank == 0:
         names = ["likelihood", "publish", "speculative_draw", "barrier_wait", "reduce", "decide", "accept_path", "batches"]
         pc = [eng.get_option("mh_prof_%d" % i) for i in range(8)]
@@ -440,7 +512,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return 0
-    tree_samples = tree_sample_rate(s, local_rank) if (world == 1 and not args.no_cpu_baseline) else None
+    tree_samples = tree_sample_rate(s, local_rank) if (world == 1 and not args.no_cpu_baseline and not args.no_tree_samples) else None
 
     # ---- roofline of the dominant kernel (mh_kernel), per launch
     its_kernel = MH_ITR / (kms * 1e-3)
@@ -470,10 +542,10 @@ def main():
                                   % (args.cpu_sample_iters, args.workload, r["t_run"], r["t_parse"], r["accept"], os.cpu_count())}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(config, l2="256 MiB L2 flush enqueued between timed steps; working set is on-chip by design",
-                                                 mh_batch=eng.get_option("mh_batch")),
-            "accept_ratio": statistics.mean(ratios), "clocks": clocks,
+            "ms_per_step": total_ms / args.steps, "mh_iterations_per_step": MH_ITR, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config,
+            "timing": {"l2": "256 MiB L2 flush enqueued between timed steps; working set is on-chip by design", "mh_batch": eng.get_option("mh_batch")},
+            "accept_ratio": statistics.mean(ratios), "clocks": clocks, "oracle_check": oracle_check, "accept_sweep": accept_sweep,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "collapsed_plain_data": collapsed,
             "tree_samples": tree_samples}

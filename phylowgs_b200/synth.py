@@ -2,6 +2,8 @@
 in `seed`; used by bench.py and the parity tests.  Values follow the conventions of the reference's
 input files (README.md:21-55, parser/create_phylowgs_inputs.py:311-345,461-475): a = reference reads,
 d = total reads, mu_r = 0.999, mu_v = 0.499, CNV rows "sK,minor,major"."""
+import os
+
 import numpy as np
 
 CN_STATES = [(2, 1), (2, 0), (1, 0), (2, 2), (3, 1)]   # (major, minor)
@@ -127,6 +129,33 @@ def config(n):
     if n == 4:
         return make_synthetic(20000, 0, 5, 8, seed=1004, frac_cnv=0.0, depth=100)
     raise ValueError("config %r is not synthetic" % (n,))
+
+
+def from_files(ssm_fn, cnv_fn, k_pops):
+    """Bench state for a data set in the reference's file formats (README.md:21-55): a chain tree root -> 1 -> ... -> k_pops, the
+    SSMs dealt to the populations by their variant-allele fraction in the first sample (equal-size bins), every CNV in
+    population 1, phi of a population = twice the mean VAF of its SSMs (made non-increasing down the chain, at most 1)."""
+    from .host.backend import arrays_from_data
+    from .host.evolve import load_data
+    codes, n_ssm, n_cnv, _ = load_data(ssm_fn, cnv_fn if cnv_fn else os.devnull)
+    arr = arrays_from_data(codes)
+    a, d = arr["a"], arr["d"]
+    D, T = a.shape
+    K = k_pops + 1
+    vaf = 1.0 - a[:n_ssm] / np.maximum(d[:n_ssm], 1)
+    order = np.argsort(-vaf[:, 0], kind="stable")
+    node = np.ones(D, dtype=np.int32)
+    for r, j in enumerate(order):
+        node[j] = 1 + min(k_pops - 1, r * k_pops // max(n_ssm, 1))
+    phi = np.ones((K, T))
+    for k in range(1, K):
+        m = vaf[node[:n_ssm] == k].mean(axis=0) if np.any(node[:n_ssm] == k) else phi[k - 1] / 2
+        phi[k] = np.minimum(np.clip(2.0 * m, 0.02, 1.0), phi[k - 1] * 0.98)
+    pi = phi.copy()
+    pi[:-1] -= phi[1:]
+    parent = np.arange(-1, K - 1, dtype=np.int32)
+    arr.update(parent=parent, node_of_datum=node, phi=phi, pi=pi)
+    return arr
 
 
 def data_kwargs(s):
