@@ -222,7 +222,7 @@ def ncu_traffic_bytes():
     return best
 
 
-def tree_sample_rate(s, device, iterations=6):
+def tree_sample_rate(s, device, iterations=6, cpu_mh=None, cpu_seconds=10.0):
     """Secondary figure of BASELINE's metric: full MCMC tree samples/s of one chain through the host glue (evolve.py:148-230:
     assignment sweep + MH + sticks/hypers + LLH trace + pickling) on the same workload, the first iteration discarded.  The
     reference's Python-2 side cannot run here, so there is no CPU number beside it (its sweep is O(N^2))."""
@@ -271,10 +271,46 @@ def tree_sample_rate(s, device, iterations=6):
     backend.close()
     med = statistics.median(times[1:])
     p = np.median(np.array(parts[1:]), axis=0)
-    return {"value": 1.0 / med, "unit": "tree samples/s", "iterations": iterations - 1, "mh_iterations_per_sample": MH_ITR,
-            "seconds": {"assignment_sweep": float(p[0]), "metropolis": float(p[1]), "sticks_hypers_llh": float(p[2]), "pickle": float(p[3])},
-            "note": "burn-in iterations from the one-node start (many spawned nodes); no CPU figure: the reference's Python-2 "
-                    "sweep cannot run here"}
+    out = {"value": 1.0 / med, "unit": "tree samples/s", "iterations": iterations - 1, "mh_iterations_per_sample": MH_ITR,
+           "seconds": {"assignment_sweep": float(p[0]), "metropolis": float(p[1]), "sticks_hypers_llh": float(p[2]), "pickle": float(p[3])},
+           "note": "burn-in iterations from the one-node start (many spawned nodes)"}
+    if cpu_mh is not None:
+        # ---- the CPU beside it ("Python half"): the reference's sweep and LLH trace, restated in plain
+        # Python with the reference's cost structure (oracle/py_half.py, held against the reference's own code by
+        # tests/test_py_half.py), on the tree the GPU chain has just reached; a bounded sample of the data, scaled to all of them
+        from oracle import py_half
+        n_data, K_now = tssb.num_data, len(tssb.get_nodes())
+        for d in codes:
+            d.node = tssb.assignments[d.index]
+        t_sw, calls, done, t0 = 0.0, 0, 0, time.perf_counter()
+        order = np.random.RandomState(2).permutation(n_data)
+        while done < n_data and (done < 4 or time.perf_counter() - t0 < cpu_seconds):
+            dt, c = py_half.sweep_sample(tssb, [int(order[done])], rng)
+            t_sw += dt
+            calls += c
+            done += 1
+        per_call = t_sw / max(calls, 1)
+        sweep_s = t_sw / done * n_data
+        llh_s = per_call * n_data                                            # complete_data_log_likelihood: one logprob per datum
+        mh_s = cpu_mh["t_parse"] + MH_ITR / cpu_mh["rate"]                   # one mh.o call as params.metropolis makes it
+        total = sweep_s + llh_s + mh_s
+        out["cpu_baseline"] = {
+            "value": 1.0 / total, "unit": "tree samples/s", "cores": 1, "kind": "port",
+            "seconds": {"assignment_sweep": sweep_s, "llh_trace": llh_s, "metropolis": mh_s},
+            "sample": "oracle/py_half.py (tssb.py:82-150, 404-410 + data.py:26-134 restated; python2 cannot run here): the sweep body "
+                      "for %d of the %d data on the %d-node tree the GPU chain reached (%.1f s, %d logprob calls, %.1f ms each: "
+                      "every call re-derives the tree metadata, data.py:33-38), scaled to all data; LLH trace = one logprob per "
+                      "datum; metropolis = one oracle/_ref/mh.o call of %d iterations at the bench tree's rate incl. its text "
+                      "re-parse; stick / hyper-parameter updates and pickling (the same host work on both sides) left out"
+                      % (done, n_data, K_now, t_sw, calls, 1e3 * per_call, MH_ITR)}
+    return out
+
+
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except (OSError, ValueError):
+        return 6650.0
 
 
 def reduce_max_over_ranks(x, world, device):
@@ -308,6 +344,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-accept-sweep", action="store_true")
     ap.add_argument("--no-oracle-check", action="store_true")
+    ap.add_argument("--no-chain-sweep", action="store_true")
+    ap.add_argument("--no-grid", action="store_true")
     ap.add_argument("--no-tree-samples", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="tuning: library option name=value (pwgs_set_option), repeatable")
     ap.add_argument("--mh-std", type=float, default=MH_STD, help="proposal concentration (evolve.py adapts it between 100 and 10000)")
@@ -483,6 +521,70 @@ def main():
             accept_sweep.append(row)
         accept_sweep.sort(key=lambda r: r["mh_std"])
 
+    # ---- 1-8 chains of this workload on ONE GPU (BASELINE.json configs[4]): one cooperative launch, 148 / C SMs per chain
+    chains_per_gpu = None
+    if rank == 0 and world == 1 and not args.no_chain_sweep:
+        chains_per_gpu = []
+        extra = []
+        try:
+            for C_ in (1, 2, 4, 8):
+                while len(extra) < C_ - 1:
+                    e2 = P.Engine(device=local_rank, **synth.data_kwargs(s))
+                    e2.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
+                    for kv in args.opt:
+                        e2.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+                    extra.append(e2)
+                engs = [eng] + extra[:C_ - 1]
+                ks = []
+                for k in range(3 + min(args.steps, 10)):
+                    with torch.cuda.stream(ext):
+                        flush.zero_()
+                    P.Engine.mh_launch_multi(engs, MH_ITR, mh_std, seed, [chain_stream(c_, 5, k) for c_ in range(C_)])
+                    rr = [e_.mh_wait(fetch=False) for e_ in engs]
+                    if k >= 3:
+                        ks.append(max(r_["kernel_ms"] for r_ in rr))
+                chains_per_gpu.append({"chains": C_, "sms_per_chain": eng.get_option("n_sms") // C_, "value": C_ * MH_ITR / (statistics.mean(ks) * 1e-3),
+                                       "unit": UNIT, "kernel_ms_per_launch": statistics.mean(ks)})
+        finally:
+            for e2 in extra:
+                e2.close()
+
+    # ---- the grid kernel K2 (SURVEY.md 8d "Grid kernel K2"): every datum in every node of a 128-node tree over the same data, the
+    # size an assignment sweep asks for at this workload (bench.py's tree samples run at 100-200 nodes); device time from the
+    # library's own events around the kernel, end-to-end time with the grid landing in page-locked host memory
+    grid_kernel = None
+    if rank == 0 and world == 1 and not args.no_grid:
+        Kg, rng_g = 128, np.random.default_rng(1)
+        parent_g = np.array([-1] + [int(rng_g.integers(0, k)) for k in range(1, Kg)], dtype=np.int32)
+        pi_g = rng_g.dirichlet(np.ones(Kg), size=T).T.copy()
+        phi_g = pi_g.copy()
+        for k in range(Kg - 1, 0, -1):
+            phi_g[parent_g[k]] += phi_g[k]
+        nod_g = rng_g.integers(1, Kg, size=D).astype(np.int32)
+        eng.set_tree(parent_g, nod_g, phi_g, pi_g)
+        buf = eng.host_buffer((Kg, D))
+        ks, es = [], []
+        for k in range(8):
+            t0 = time.perf_counter()
+            eng.llh_range(0, D, None, P.SEM_PY, col_major=True, out=buf)
+            es.append(time.perf_counter() - t0)
+            ks.append(eng.get_option("grid_kernel_ns") * 1e-9)
+        k_s, e_s = statistics.median(ks[2:]), statistics.median(es[2:])
+        pairs = D * Kg
+        n_plain_pairs, n_cnv_pairs = (D - M) * Kg, M * Kg
+        # FP64-pipe instructions of the kernel as compiled (libm log / exp: profiles/r02_pair_llh_kernel_sass_histogram.txt):
+        # a plain pair = 2 logs (29 each) + 8; a CNV-affected pair (data.py convention) ~ 2-4 states x (2 logs + division 13 + 8)
+        # + logsumexp (exp 16 each + log 29) ~ 400 per sample
+        fp_grid = T * (n_plain_pairs * 66.0 + n_cnv_pairs * 400.0)
+        by_grid = D * (20 + 8 * T) + 8.0 * pairs
+        eng.set_tree(s["parent"], s["node_of_datum"], s["phi"], s["pi"])
+        grid_kernel = {"pairs": pairs, "tree_nodes": Kg, "kernel_ms": 1e3 * k_s, "e2e_ms": 1e3 * e_s, "pairs_per_s": pairs / k_s,
+                       "d2h_bytes": 8 * pairs,
+                       "roofline": {"bound": "fp64", "achieved": fp_grid / k_s / 1e9, "peak": fp64_peak / 1e9, "unit": "G FP64-instr/s",
+                                    "frac": fp_grid / k_s / fp64_peak,
+                                    "hbm": {"achieved": by_grid / k_s / 1e9, "peak": hbm_peak_gbs(), "unit": "GB/s", "frac": by_grid / k_s / 1e9 / hbm_peak_gbs()},
+                                    "pcie_d2h_GBps_e2e": 8 * pairs / e_s / 1e9}}
+
     if args.profile_phases and rank == 0:
         names = ["likelihood", "publish", "speculative_draw", "barrier_wait", "reduce", "decide", "accept_path", "batches"]
         pc = [eng.get_option("mh_prof_%d" % i) for i in range(8)]
@@ -512,7 +614,12 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return 0
-    tree_samples = tree_sample_rate(s, local_rank) if (world == 1 and not args.no_cpu_baseline and not args.no_tree_samples) else None
+    tree_samples = None
+    if world == 1 and not args.no_tree_samples:
+        cpu_mh = None if args.no_cpu_baseline else time_reference(s, 1, args.cpu_sample_iters, mh_std)
+        tree_samples = tree_sample_rate(s, local_rank, cpu_mh=cpu_mh)
+    else:
+        cpu_mh = None
 
     # ---- roofline of the dominant kernel (mh_kernel), per launch
     its_kernel = MH_ITR / (kms * 1e-3)
@@ -535,7 +642,7 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        r = time_reference(s, 1, args.cpu_sample_iters, mh_std)
+        r = cpu_mh or time_reference(s, 1, args.cpu_sample_iters, mh_std)
         cpu_baseline = {"value": r["rate"], "unit": UNIT, "cores": 1, "kind": "reference",
                         "sample": "oracle/_ref/mh.o (unmodified mh.cpp+util.cpp, g++ -O3, GSL shim) MH_ITR=%d on the same %s inputs: %.2fs total, "
                                   "%.2fs of it the per-call text re-parse (excluded from the rate); accept=%.4f; host has %d cores"
@@ -545,7 +652,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "mh_iterations_per_step": MH_ITR, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
             "timing": {"l2": "256 MiB L2 flush enqueued between timed steps; working set is on-chip by design", "mh_batch": eng.get_option("mh_batch")},
-            "accept_ratio": statistics.mean(ratios), "clocks": clocks, "oracle_check": oracle_check, "accept_sweep": accept_sweep,
+            "accept_ratio": statistics.mean(ratios), "clocks": clocks, "oracle_check": oracle_check, "accept_sweep": accept_sweep, "chains_per_gpu": chains_per_gpu, "grid_kernel": grid_kernel,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "collapsed_plain_data": collapsed,
             "tree_samples": tree_samples}

@@ -35,7 +35,7 @@ enum {
     PWGS_EINVAL = -1,   /* bad argument (message says which) */
     PWGS_ECUDA = -2,    /* CUDA runtime error / no device */
     PWGS_ESTATE = -3,   /* call order (e.g. mh_run before set_tree) */
-    PWGS_ELIMIT = -4    /* problem exceeds a documented limit (K*T shared-memory budget, copy numbers > 32767) */
+    PWGS_ELIMIT = -4    /* problem exceeds a documented limit (copy numbers > 32767, more than ~20 000 tree nodes) */
 };
 
 /* Likelihood conventions. */
@@ -72,8 +72,21 @@ int pwgs_destroy(pwgs_ctx *ctx);
  *   parent        [K]  parent index, -1 for the single root; any node order
  *   node_of_datum [D]  node holding each datum
  *   phi, pi       [K*T] row-major [node][sample]  (node.params, node.pi) */
-int pwgs_set_tree(pwgs_ctx *ctx, int K, const int32_t *parent, const int32_t *node_of_datum,
+int pwgs_set_tree(pwgs_ctx *ctx, int K, const int32_t *parent, const int32_t *node_of_datum /* or NULL, see pwgs_move_data */,
                   const double *phi, const double *pi);
+
+/* Tree edits in the middle of an assignment sweep (tssb.py:122-124 moves a datum, find_node tssb.py:353-361 spawns nodes) without
+ * re-sending what did not change:
+ *  - pwgs_set_tree with node_of_datum == NULL keeps the assignments the device already has (allowed when the new tree has at
+ *    least as many nodes as the last one: spawned nodes are appended and hold no data yet);
+ *  - pwgs_move_data re-assigns n data: datum[i] now sits in node[i].
+ * Both only queue work on the context's stream (no host synchronisation). */
+int pwgs_move_data(pwgs_ctx *ctx, int n, const int32_t *datum, const int32_t *node);
+
+/* A page-locked host buffer of at least `bytes`, owned by the context (valid until the next call with a larger size or
+ * pwgs_destroy).  Output arrays that live in it (the datum x node grid of a sweep, 45 MB at 50k SSMs x 110 nodes) are written by
+ * DMA at PCIe speed; results written to ordinary pageable memory go through the driver's staging copy (4x slower). */
+int pwgs_host_buffer(pwgs_ctx *ctx, uint64_t bytes, void **ptr);
 
 /* Replaces `mh.o` (mh.cpp:22-109) as invoked by params.metropolis (params.py:30-65): `iters`
  * Metropolis-Hastings iterations over (pi, phi) for the tree of the last pwgs_set_tree, in ONE
@@ -92,6 +105,13 @@ int pwgs_mh_launch(pwgs_ctx *ctx, int iters, double mh_std, uint64_t seed, uint6
 int pwgs_mh_wait(pwgs_ctx *ctx, double *phi_out, double *pi_out, double *accept_ratio, double *llh_out,
                  float *kernel_ms);
 
+/* Several chains of ONE device in one cooperative launch (multievolve.py:85-105 runs its chains as independent processes, whose
+ * kernels time-slice the GPU; small inputs leave most of it idle): chain i gets n_sms / n_chains CTAs and runs exactly what
+ * pwgs_mh_launch would with "mh_ctas" set to that number -- same random streams, same result bits.  Every context then takes its
+ * own pwgs_mh_wait.  mh_std, seed, stream: [n_chains]. */
+int pwgs_mh_launch_multi(int n_chains, pwgs_ctx *const *ctxs, int iters, const double *mh_std, const uint64_t *seed,
+                         const uint64_t *stream);
+
 /* Replaces Datum._log_likelihood as called per candidate node by TSSB.resample_assignments
  * (tssb.py:111,128 -> alleles.py:52 -> data.py:26-62): out[r*K + k] = log-likelihood of datum rows[r]
  * if it sat in node k of the current tree (all K candidates at once). */
@@ -100,6 +120,8 @@ int pwgs_llh_rows(pwgs_ctx *ctx, int n_rows, const int32_t *rows, int semantics,
  * spawns nodes (tssb.py:353-361) only the new nodes' columns are missing: a spawn splits its parent's pi but leaves every
  * existing node's phi, and therefore every existing grid entry, unchanged. */
 int pwgs_llh_block(pwgs_ctx *ctx, int n_rows, const int32_t *rows, int n_cols, const int32_t *cols, int semantics, double *out);
+/* The same for the data row0 .. row0 + n_rows - 1 (the data an assignment sweep has still to visit): no row list to send. */
+int pwgs_llh_range(pwgs_ctx *ctx, int row0, int n_rows, int n_cols, const int32_t *cols, int semantics, double *out);
 
 /* semantics MH: multi_param_post of the current state (mh.cpp:147-166).
  * semantics PY: the data term of TSSB.complete_data_log_likelihood (tssb.py:404-410, alleles.py:55-56). */
@@ -114,7 +136,8 @@ int pwgs_get_data_states(pwgs_ctx *ctx, int32_t *M, int32_t *ssm_of_m, int32_t *
 /* Tuning knobs: "mh_batch" (largest speculative batch of proposals per grid barrier: a power of two in 1..256 = default; the kernel
  * adapts the actual batch to the running acceptance rate), "mh_ctas" (CTAs per chain, 0 = all SMs) and "mh_collapse" (1: plain
  * data enter the MH likelihood through exact integer totals per (node, error-rate class, sample) instead of one term per datum;
- * off by default, available when the data have at most 16 distinct (mu_r, mu_v) pairs).  "mh_w_plain", "mh_w_cnv1", "mh_w_cnv2",
+ * off by default, available when the data have at most 16 distinct (mu_r, mu_v) pairs), "mh_big" (-1 = automatic: trees whose
+ * node tables (about 18 K T doubles) do not fit in shared memory keep them in global memory; 1 / 0 force / forbid that).  "mh_w_plain", "mh_w_cnv1", "mh_w_cnv2",
  * "mh_w_cnv3": relative cost of a warp round (32 data) of plain data / of CNV-affected SSMs with 1, 2, 3 merged states, used to
  * deal whole rounds to the chain's CTAs (defaults 100 / 183 / 429 / 675, fitted to measured per-CTA cycles).  Diagnostics with
  * "mh_profile" = 1: "mh_prof_0".."mh_prof_7" (CTA 0's cycles per phase), "mh_lik_min/max/sum" and "mh_lik_cta_<r>" (likelihood

@@ -26,9 +26,13 @@ SIGNATURES = {
     "pwgs_set_tree": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p, _f64p, _f64p]),
     "pwgs_mh_run": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, _f64p, _f64p, _f64p, _f64p]),
     "pwgs_mh_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64]),
+    "pwgs_mh_launch_multi": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int, _f64p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pwgs_mh_wait": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, _f64p, C.POINTER(C.c_float)]),
     "pwgs_llh_rows": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, _f64p]),
     "pwgs_llh_block": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _f64p]),
+    "pwgs_llh_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _f64p]),
+    "pwgs_move_data": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p]),
+    "pwgs_host_buffer": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "pwgs_total_llh": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
     "pwgs_get_lbc": (C.c_int, [C.c_void_p, _f64p]),
     "pwgs_get_data_states": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p]),

@@ -43,10 +43,32 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// page-locked host memory (DMA without the runtime's staging copy; copies from / to it are truly asynchronous)
+struct PinnedBuf {
+    char *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t bytes)
+    {
+        if (bytes <= n && p) return cudaSuccess;
+        release();
+        n = bytes ? bytes : 1;
+        cudaError_t e = cudaHostAlloc((void **)&p, n, cudaHostAllocDefault);
+        if (e != cudaSuccess) { p = nullptr; n = 0; }
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
 struct pwgs_ctx {
     int device = 0, n_sms = 0;
+    PinnedBuf stage;                                      // pwgs_set_tree / pwgs_move_data / row lists: host side of the uploads
+    cudaEvent_t stage_ev = nullptr;                       // recorded after the last copy out of `stage`
+    bool stage_busy = false;
+    PinnedBuf user_buf;                                   // pwgs_host_buffer
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;             // around the last grid kernel (option "grid_kernel_ns")
+    bool grid_timed = false;
     // ---- data set
     int n_ssm = 0, n_cnv = 0, T = 0, D = 0, Dp = 0, M = 0, L = 0;
     std::vector<int> ssm_of_m;
@@ -88,7 +110,8 @@ struct pwgs_ctx {
     int prof_cpc = 0;
     DevBuf<int> acc_out, rows, cols, abort_flag;
     DevBuf<MhParams> plist;
-    int opt_batch = PWGS_MAX_BATCH, opt_ctas = 0, opt_stage = 1, opt_dist = -1;
+    int opt_batch = PWGS_MAX_BATCH, opt_ctas = 0, opt_stage = 1, opt_dist = -1, opt_big = -1;
+    DevBuf<double> gscratch;                               // mh_kernel<false, true>: the CTAs' node tables in global memory
     bool launched = false;
     int launched_iters = 0;
     long long n_launches = 0;                             // kernels of this library launched on behalf of the context
@@ -196,9 +219,13 @@ int pwgs_destroy(pwgs_ctx *c)
     c->code_tmp.release(); c->enode_tmp.release(); c->pos.release(); c->w_a.release(); c->w_d.release(); c->w_code.release();
     c->w_enode.release(); c->overflow.release(); c->plan.release(); c->ecoef_tmp.release(); c->w_ecoef.release(); c->w_lbc.release(); c->w_mu_r.release();
     c->sums.release(); c->phisub.release(); c->ring.release(); c->phi_out.release(); c->pi_out.release(); c->llh_out.release(); c->scratch.release();
-    c->counter.release(); c->prof.release(); c->acc_out.release(); c->abort_flag.release(); c->cols.release(); c->rows.release(); c->plist.release();
+    c->counter.release(); c->prof.release(); c->acc_out.release(); c->abort_flag.release(); c->cols.release(); c->rows.release(); c->plist.release(); c->gscratch.release();
+    c->stage.release(); c->user_buf.release();
+    if (c->stage_ev) cudaEventDestroy(c->stage_ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return PWGS_OK;
@@ -255,6 +282,9 @@ int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
     CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaEventCreate(&c->ev0));
     CREATE_TRY(cudaEventCreate(&c->ev1));
+    CREATE_TRY(cudaEventCreate(&c->ev2));
+    CREATE_TRY(cudaEventCreate(&c->ev3));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming));
     cudaStream_t s = c->stream;
 
     std::vector<int> zero_ptr(n_ssm + 1, 0), dummy(1, 0);
@@ -344,12 +374,26 @@ int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
     return PWGS_OK;
 }
 
+// the staging buffer may be rewritten once the copies of the previous user have left it
+static cudaError_t stage_acquire(pwgs_ctx *c, size_t bytes)
+{
+    if (c->stage_busy) { cudaError_t e = cudaEventSynchronize(c->stage_ev); if (e != cudaSuccess) return e; c->stage_busy = false; }
+    return c->stage.alloc(bytes);
+}
+static cudaError_t stage_release(pwgs_ctx *c)
+{
+    c->stage_busy = true;
+    return cudaEventRecord(c->stage_ev, c->stream);
+}
+
 int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node_of_datum,
                   const double *phi, const double *pi)
 {
     if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
     if (K <= 0 || K > 65535) return fail(PWGS_EINVAL, "K must be in 1..65535");
-    if (!parent || !node_of_datum || !phi || !pi) return fail(PWGS_EINVAL, "NULL array");
+    if (!parent || !phi || !pi) return fail(PWGS_EINVAL, "NULL array");
+    if (!node_of_datum && (!c->tree_set || K < c->K))
+        return fail(PWGS_EINVAL, "node_of_datum may only be NULL (= keep the device's assignments) after a tree with at most K nodes was set");
     HostTree ht;
     {
         std::string err;
@@ -358,34 +402,83 @@ int pwgs_set_tree(pwgs_ctx *c, int K, const int32_t *parent, const int32_t *node
     for (size_t i = 0; i < (size_t)K * c->T; i++)
         if (!(phi[i] >= 0.0 && phi[i] <= 1.000001 && pi[i] >= 0.0 && pi[i] <= 1.000001))
             return fail(PWGS_EINVAL, "phi and pi must lie in [0,1] (node " + std::to_string(i / c->T) + ")");
-    for (int j = 0; j < c->D; j++)
-        if (node_of_datum[j] < 0 || node_of_datum[j] >= K) return fail(PWGS_EINVAL, "node_of_datum out of range at datum " + std::to_string(j));
-    const std::vector<int> &depth = ht.depth, &tin = ht.tin, &tout = ht.tout, &order = ht.order;
+    if (node_of_datum)
+        for (int j = 0; j < c->D; j++)
+            if (node_of_datum[j] < 0 || node_of_datum[j] >= K) return fail(PWGS_EINVAL, "node_of_datum out of range at datum " + std::to_string(j));
 
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const int T = c->T;
+    const size_t KT = (size_t)K * T;
+    // One page-locked staging area, plain asynchronous copies out of it, no synchronisation: an assignment sweep calls this
+    // about a hundred times (every spawn event), and uploads from pageable memory synchronise the stream once per array.
+    const size_t nd = 3 * KT, ni = 5 * (size_t)K + (node_of_datum ? (size_t)c->D : 0);
+    CUDA_TRY(stage_acquire(c, nd * sizeof(double) + ni * sizeof(int)));
+    double *hd = (double *)c->stage.p;
+    int *hi = (int *)(hd + nd);
+    memcpy(hd, phi, KT * sizeof(double)); memcpy(hd + KT, pi, KT * sizeof(double)); memcpy(hd + 2 * KT, ht.phisub.data(), KT * sizeof(double));
+    memcpy(hi, parent, K * sizeof(int)); memcpy(hi + K, ht.depth.data(), K * sizeof(int)); memcpy(hi + 2 * K, ht.tin.data(), K * sizeof(int));
+    memcpy(hi + 3 * K, ht.tout.data(), K * sizeof(int)); memcpy(hi + 4 * (size_t)K, ht.order.data(), K * sizeof(int));
+    if (node_of_datum) memcpy(hi + 5 * (size_t)K, node_of_datum, (size_t)c->D * sizeof(int));
     c->K = K;
-    CUDA_TRY(c->parent.upload(parent, K, s));
-    CUDA_TRY(c->depth.upload(depth.data(), K, s));
-    CUDA_TRY(c->tin.upload(tin.data(), K, s));
-    CUDA_TRY(c->tout.upload(tout.data(), K, s));
-    CUDA_TRY(c->order.upload(order.data(), K, s));
-    CUDA_TRY(c->node_of_datum.upload(node_of_datum, c->D, s));
-    CUDA_TRY(c->phi.upload(phi, (size_t)K * T, s));
-    CUDA_TRY(c->pi.upload(pi, (size_t)K * T, s));
-    CUDA_TRY(c->phisub.upload(ht.phisub.data(), (size_t)K * T, s));
+    CUDA_TRY(c->phi.upload(hd, KT, s));
+    CUDA_TRY(c->pi.upload(hd + KT, KT, s));
+    CUDA_TRY(c->phisub.upload(hd + 2 * KT, KT, s));
+    CUDA_TRY(c->parent.upload(hi, K, s));
+    CUDA_TRY(c->depth.upload(hi + K, K, s));
+    CUDA_TRY(c->tin.upload(hi + 2 * K, K, s));
+    CUDA_TRY(c->tout.upload(hi + 3 * K, K, s));
+    CUDA_TRY(c->order.upload(hi + 4 * (size_t)K, K, s));
+    if (node_of_datum) CUDA_TRY(c->node_of_datum.upload(hi + 5 * (size_t)K, c->D, s));
+    CUDA_TRY(stage_release(c));
     c->root = ht.root;
-    CUDA_TRY(c->phi_out.alloc((size_t)K * T));
-    CUDA_TRY(c->pi_out.alloc((size_t)K * T));
-    if (c->Dp > 0) {
+    CUDA_TRY(c->phi_out.alloc(KT));
+    CUDA_TRY(c->pi_out.alloc(KT));
+    if (node_of_datum && c->Dp > 0) {
         gather_node_kernel<<<(c->Dp + 255) / 256, 256, 0, s>>>(c->Dp, c->pidx.p, c->node_of_datum.p, c->pnode.p);
         c->n_launches++;
         CUDA_TRY(cudaGetLastError());
     }
     c->work_valid = false;
-    CUDA_TRY(cudaStreamSynchronize(s));   // host arrays (incl. local vectors) may go away after return
     c->tree_set = true;
+    return PWGS_OK;
+}
+
+int pwgs_move_data(pwgs_ctx *c, int n, const int32_t *datum, const int32_t *node)
+{
+    if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
+    if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called first");
+    if (n < 0 || (n > 0 && (!datum || !node))) return fail(PWGS_EINVAL, "pwgs_move_data: NULL array");
+    for (int i = 0; i < n; i++)
+        if (datum[i] < 0 || datum[i] >= c->D || node[i] < 0 || node[i] >= c->K) return fail(PWGS_EINVAL, "pwgs_move_data: index out of range");
+    if (n == 0) return PWGS_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(stage_acquire(c, 2 * (size_t)n * sizeof(int)));
+    int *h = (int *)c->stage.p;
+    memcpy(h, datum, n * sizeof(int)); memcpy(h + n, node, n * sizeof(int));
+    CUDA_TRY(c->rows.alloc(2 * (size_t)n));
+    CUDA_TRY(cudaMemcpyAsync(c->rows.p, h, 2 * (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(stage_release(c));
+    move_data_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->rows.p, c->rows.p + n, c->node_of_datum.p);
+    CUDA_TRY(cudaGetLastError());
+    c->n_launches++;
+    if (c->Dp > 0) {
+        gather_node_kernel<<<(c->Dp + 255) / 256, 256, 0, c->stream>>>(c->Dp, c->pidx.p, c->node_of_datum.p, c->pnode.p);
+        CUDA_TRY(cudaGetLastError());
+        c->n_launches++;
+    }
+    c->work_valid = false;
+    return PWGS_OK;
+}
+
+int pwgs_host_buffer(pwgs_ctx *c, uint64_t bytes, void **ptr)
+{
+    if (!c || !ptr) return fail(PWGS_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));          // nothing may still be writing into the buffer it replaces
+    // page-locking is slow (~1 ms per MB): grow with headroom so that a tree that gains a few nodes does not pay it again
+    if (bytes > c->user_buf.n || !c->user_buf.p) CUDA_TRY(c->user_buf.alloc(bytes + bytes / 2));
+    *ptr = c->user_buf.p;
     return PWGS_OK;
 }
 
@@ -544,25 +637,41 @@ static size_t mh_smem_bytes(int K, int T, int B)
     return mh_smem_doubles(K, T, B) * sizeof(double) + mh_smem_ints(K) * sizeof(int) + 16;
 }
 
-extern "C" {
-
-int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_t stream)
+// One chain's share of an MH launch: batch size, work partition for cpc CTAs, buffers, descriptor.  kind: 0 = data slice staged in
+// shared memory, 1 = read in place, 2 = tree-sized tables in global memory (BIG).
+struct MhPlan { MhParams p; size_t smem; int kind; };
+static const void *mh_kernel_of(int kind)
+{
+    return kind == 0 ? (const void *)mh_kernel<true, false> : kind == 1 ? (const void *)mh_kernel<false, false> : (const void *)mh_kernel<false, true>;
+}
+static int mh_prepare(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_t stream, int cpc, MhPlan &plan)
 {
     if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
     if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called before pwgs_mh_run");
+    if (c->launched) return fail(PWGS_ESTATE, "an MH launch is pending: call pwgs_mh_wait first");
     if (iters < 0) return fail(PWGS_EINVAL, "iters must be >= 0");
     if (!(mh_std > 0)) return fail(PWGS_EINVAL, "mh_std must be > 0");
     CUDA_TRY(cudaSetDevice(c->device));
     int B = c->opt_batch;
-    int cpc = c->opt_ctas > 0 ? std::min(c->opt_ctas, c->n_sms) : c->n_sms;
     size_t smem = mh_smem_bytes(c->K, c->T, B);
     while (smem > 176 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B); }
-    if (smem > 200 * 1024) return fail(PWGS_ELIMIT, "K*T too large for the shared-memory node table");
+    // Trees whose node tables leave no room for a batch of MH_BU proposals in shared memory (K*T beyond ~600) run with the
+    // tables in global memory: slower per iteration, but no limit short of device memory (the reference has none either).
+    const bool big = c->opt_big > 0 || (c->opt_big < 0 && (B < MH_BU || smem > 200 * 1024));
+    size_t gstride = 0;
+    if (big) {
+        B = c->opt_batch;
+        while (B > MH_BU && mh_tree_doubles(c->K, c->T, B) * sizeof(double) > ((size_t)8 << 20)) B >>= 1;   // <= 8 MiB per CTA
+        gstride = (mh_tree_doubles(c->K, c->T, B) + 1) & ~(size_t)1;
+        smem = mh_fixed_doubles(B) * sizeof(double) + mh_smem_ints(c->K) * sizeof(int) + 16;
+        if (smem > 200 * 1024) return fail(PWGS_ELIMIT, "tree too large: the Euler-tour table of K nodes exceeds shared memory");
+        CUDA_TRY(c->gscratch.alloc(gstride * cpc));
+    }
     const int collapse = (c->opt_collapse && c->n_classes > 0 && c->Dp > 0) ? c->n_classes : 0;
     { int rc_ = prepare_cnv_work(c, cpc, collapse, mh_group_classes(B)); if (rc_ != PWGS_OK) return rc_; }
     // stage each CTA's slice of the data in shared memory when it fits beside the node tables
     const size_t stage_bytes = mh_stage_bytes(c->pchunk, c->work.cchunk, c->T, c->work.Emax) + 16;
-    const int stage = (c->opt_stage && smem + stage_bytes <= 224 * 1024) ? 1 : 0;
+    const int stage = (!big && c->opt_stage && smem + stage_bytes <= 224 * 1024) ? 1 : 0;
     if (stage) smem += stage_bytes;
     CUDA_TRY(c->sums.alloc((size_t)2 * PWGS_MAX_BATCH * MH_SUM_STRIDE));
     CUDA_TRY(cudaMemsetAsync(c->sums.p, 0, (size_t)2 * PWGS_MAX_BATCH * MH_SUM_STRIDE * sizeof(unsigned long long), c->stream));
@@ -579,7 +688,7 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
         CUDA_TRY(cudaGetLastError());
         c->n_launches++;
     }
-    MhParams p;
+    MhParams &p = plan.p;
     p.Dp = c->Dp; p.M = c->M; p.T = c->T; p.K = c->K;
     p.n_classes = collapse; p.cl_sums = c->cl_sums.p; p.cl_mu_r = c->cl_mu_r.p; p.cl_mu_v = c->cl_mu_v.p;
     p.pa = c->pa.p; p.pd = c->pd.p; p.pmu_r = c->pmu_r.p; p.pmu_v = c->pmu_v.p; p.pnode = c->pnode.p;
@@ -591,42 +700,105 @@ int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_
     p.seed = seed; p.stream = stream;
     p.sums = c->sums.p; p.ring = c->ring.p; p.counter = c->counter.p; p.abort_flag = c->abort_flag.p;
     p.lbc_plain_sum = c->lbc_plain_sum; p.log_tiny = kLogTinyMh;
+    p.gscratch = big ? c->gscratch.p : nullptr; p.gstride = gstride;
     p.prof = nullptr;
     if (c->opt_prof) { CUDA_TRY(c->prof.alloc(16 + 256)); p.prof = c->prof.p; c->prof_cpc = std::min(cpc, 256); }
-    // pageable source: the runtime stages the bytes before returning, so the stack object is safe
-    CUDA_TRY(cudaMemcpyAsync(c->plist.p, &p, sizeof(p), cudaMemcpyHostToDevice, c->stream));
+    plan.smem = smem;
+    plan.kind = big ? 2 : (stage ? 0 : 1);
+    return PWGS_OK;
+}
 
-    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    const void *kfn = stage ? (const void *)mh_kernel<true> : (const void *)mh_kernel<false>;
+// cooperative launch of n_chains * cpc CTAs on `s`; plist: device array of the chains' descriptors
+static int mh_launch_grid(int device, int kind, const MhParams *plist, int n_chains, int cpc, size_t smem, cudaStream_t s)
+{
+    const void *kfn = mh_kernel_of(kind);
     // the attribute belongs to the function, not to the launch: chains running as threads of one process launch with
     // different sizes concurrently, so it is always set to the one value every launch fits under
     int smem_optin = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     cudaFuncAttributes kattr;
     CUDA_TRY(cudaFuncGetAttributes(&kattr, kfn));
     const int smem_dyn_max = smem_optin - (int)kattr.sharedSizeBytes;      // the limit covers static + dynamic
     if (smem > (size_t)smem_dyn_max) return fail(PWGS_ELIMIT, "shared-memory node table exceeds the device's per-block limit");
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dyn_max);
     if (e == cudaSuccess) {
-        const MhParams *plist = c->plist.p;
         void *args[] = {(void *)&plist, (void *)&cpc};
-        e = cudaLaunchCooperativeKernel(kfn, dim3(cpc), dim3(MH_THREADS), args, smem, c->stream);
+        e = cudaLaunchCooperativeKernel(kfn, dim3(n_chains * cpc), dim3(MH_THREADS), args, smem, s);
     }
     if (e != cudaSuccess) {
         cudaFuncAttributes fa;
         int occ = -1;
         cudaGetLastError();
         cudaFuncGetAttributes(&fa, kfn);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_kernel<true>, MH_THREADS, smem);
-        return fail(PWGS_ECUDA, std::string("mh_kernel launch: ") + cudaGetErrorString(e) + " (grid " + std::to_string(cpc) + " x " +
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, MH_THREADS, smem);
+        return fail(PWGS_ECUDA, std::string("mh_kernel launch: ") + cudaGetErrorString(e) + " (grid " + std::to_string(n_chains * cpc) + " x " +
                     std::to_string(MH_THREADS) + " threads, " + std::to_string(smem) + " B dynamic smem, " + std::to_string(fa.numRegs) +
                     " regs, maxThreadsPerBlock " + std::to_string(fa.maxThreadsPerBlock) + ", static smem " + std::to_string(fa.sharedSizeBytes) +
                     ", local " + std::to_string(fa.localSizeBytes) + ", occupancy " + std::to_string(occ) + " CTA/SM)");
     }
+    return PWGS_OK;
+}
+
+extern "C" {
+
+int pwgs_mh_launch(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_t stream)
+{
+    if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
+    const int cpc = c->opt_ctas > 0 ? std::min(c->opt_ctas, c->n_sms) : c->n_sms;
+    MhPlan plan;
+    { int rc_ = mh_prepare(c, iters, mh_std, seed, stream, cpc, plan); if (rc_ != PWGS_OK) return rc_; }
+    // pageable source: the runtime stages the bytes before returning, so the stack object is safe
+    CUDA_TRY(cudaMemcpyAsync(c->plist.p, &plan.p, sizeof(MhParams), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    { int rc_ = mh_launch_grid(c->device, plan.kind, c->plist.p, 1, cpc, plan.smem, c->stream); if (rc_ != PWGS_OK) return rc_; }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->n_launches++;
     c->launched = true;
     c->launched_iters = iters;
+    return PWGS_OK;
+}
+
+int pwgs_mh_launch_multi(int n_chains, pwgs_ctx *const *ctxs, int iters, const double *mh_std, const uint64_t *seed, const uint64_t *stream)
+{
+    if (n_chains < 1 || !ctxs || !mh_std || !seed || !stream) return fail(PWGS_EINVAL, "pwgs_mh_launch_multi: NULL argument or no chains");
+    for (int i = 0; i < n_chains; i++) {
+        if (!ctxs[i]) return fail(PWGS_EINVAL, "ctx is NULL");
+        if (ctxs[i]->device != ctxs[0]->device) return fail(PWGS_EINVAL, "pwgs_mh_launch_multi: all contexts must live on one device");
+        for (int j = 0; j < i; j++) if (ctxs[j] == ctxs[i]) return fail(PWGS_EINVAL, "pwgs_mh_launch_multi: a context appears twice");
+    }
+    pwgs_ctx *c0 = ctxs[0];
+    if (n_chains > c0->n_sms) return fail(PWGS_ELIMIT, "more chains than SMs");
+    int cpc = c0->n_sms / n_chains;
+    if (c0->opt_ctas > 0) cpc = std::min(cpc, c0->opt_ctas);
+    std::vector<MhParams> plist(n_chains);
+    size_t smem = 0;
+    int kind = 0;
+    for (int i = 0; i < n_chains; i++) {
+        MhPlan plan;
+        int rc_ = mh_prepare(ctxs[i], iters, mh_std[i], seed[i], stream[i], cpc, plan);
+        if (rc_ != PWGS_OK) return rc_;
+        plist[i] = plan.p;
+        smem = std::max(smem, plan.smem);
+        kind = std::max(kind, plan.kind);                // one kernel for all chains: the most general variant any of them needs
+    }
+    if (kind == 2) for (int i = 0; i < n_chains; i++) if (!plist[i].gscratch)
+        return fail(PWGS_ELIMIT, "pwgs_mh_launch_multi: chains with and without shared-memory node tables cannot share a launch");
+    // everything the chains' own streams have queued (tree uploads, work lists) before the kernel; their later work after it
+    CUDA_TRY(c0->plist.alloc(n_chains));
+    for (int i = 1; i < n_chains; i++) {
+        CUDA_TRY(cudaEventRecord(ctxs[i]->ev0, ctxs[i]->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c0->stream, ctxs[i]->ev0, 0));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c0->plist.p, plist.data(), n_chains * sizeof(MhParams), cudaMemcpyHostToDevice, c0->stream));
+    for (int i = 0; i < n_chains; i++) CUDA_TRY(cudaEventRecord(ctxs[i]->ev0, c0->stream));
+    { int rc_ = mh_launch_grid(c0->device, kind, c0->plist.p, n_chains, cpc, smem, c0->stream); if (rc_ != PWGS_OK) return rc_; }
+    for (int i = 0; i < n_chains; i++) {
+        CUDA_TRY(cudaEventRecord(ctxs[i]->ev1, c0->stream));
+        if (i) CUDA_TRY(cudaStreamWaitEvent(ctxs[i]->stream, ctxs[i]->ev1, 0));
+        ctxs[i]->launched = true;
+        ctxs[i]->launched_iters = iters;
+    }
+    c0->n_launches++;
     return PWGS_OK;
 }
 
@@ -662,32 +834,56 @@ int pwgs_mh_run(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_t s
 }
 
 // ------------------------------------------------------------------ likelihood grid / totals
-int pwgs_llh_block(pwgs_ctx *c, int n_rows, const int32_t *rows, int n_cols, const int32_t *cols, int semantics, double *out)
+static int llh_block_impl(pwgs_ctx *c, int row0, int n_rows, const int32_t *rows, int n_cols, const int32_t *cols, int semantics, double *out)
 {
     if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
     if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called first");
-    if (n_rows < 0 || (n_rows > 0 && (!rows || !out))) return fail(PWGS_EINVAL, "rows/out NULL");
+    if (n_rows < 0 || (n_rows > 0 && !out)) return fail(PWGS_EINVAL, "rows/out NULL");
     const int col_major = (semantics & PWGS_LAYOUT_COLS) ? 1 : 0;
     semantics &= ~PWGS_LAYOUT_COLS;
     if (semantics != PWGS_SEM_MH && semantics != PWGS_SEM_PY) return fail(PWGS_EINVAL, "unknown semantics");
     if (cols == nullptr) n_cols = c->K;
     if (n_cols < 0) return fail(PWGS_EINVAL, "n_cols must be >= 0");
     if (n_rows == 0 || n_cols == 0) return PWGS_OK;
-    for (int r = 0; r < n_rows; r++) if (rows[r] < 0 || rows[r] >= c->D) return fail(PWGS_EINVAL, "row index out of range");
+    if (rows) { for (int r = 0; r < n_rows; r++) if (rows[r] < 0 || rows[r] >= c->D) return fail(PWGS_EINVAL, "row index out of range"); }
+    else if (row0 < 0 || row0 > c->D - n_rows) return fail(PWGS_EINVAL, "row range out of range");
     if (cols) for (int k = 0; k < n_cols; k++) if (cols[k] < 0 || cols[k] >= c->K) return fail(PWGS_EINVAL, "node index out of range");
     CUDA_TRY(cudaSetDevice(c->device));
     size_t total = (size_t)n_rows * n_cols;
-    CUDA_TRY(c->rows.upload(rows, n_rows, c->stream));
-    if (cols) CUDA_TRY(c->cols.upload(cols, n_cols, c->stream));
+    // row / column lists through the page-locked staging area (no implicit stream synchronisation)
+    const size_t nr = rows ? (size_t)n_rows : 0, nc = cols ? (size_t)n_cols : 0;
+    if (nr + nc) {
+        CUDA_TRY(stage_acquire(c, (nr + nc) * sizeof(int)));
+        int *h = (int *)c->stage.p;
+        if (nr) memcpy(h, rows, nr * sizeof(int));
+        if (nc) memcpy(h + nr, cols, nc * sizeof(int));
+        CUDA_TRY(c->rows.alloc(nr + nc));
+        CUDA_TRY(cudaMemcpyAsync(c->rows.p, h, (nr + nc) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(stage_release(c));
+    }
     CUDA_TRY(c->scratch.alloc(total));
-    pair_llh_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(data_view(c), tree_view(c), 0, n_rows, c->rows.p, n_cols,
-                                                                            cols ? c->cols.p : nullptr, col_major, semantics, kLogTinyMh, kLogTinyPy,
+    CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
+    pair_llh_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(data_view(c), tree_view(c), 0, row0, n_rows, rows ? c->rows.p : nullptr, n_cols,
+                                                                            cols ? c->rows.p + nr : nullptr, col_major, semantics, kLogTinyMh, kLogTinyPy,
                                                                             kLogQuarter, c->scratch.p);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev3, c->stream));
     c->n_launches++;
     CUDA_TRY(cudaMemcpyAsync(out, c->scratch.p, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->grid_timed = true;
     return PWGS_OK;
+}
+
+int pwgs_llh_block(pwgs_ctx *c, int n_rows, const int32_t *rows, int n_cols, const int32_t *cols, int semantics, double *out)
+{
+    if (n_rows > 0 && !rows) return fail(PWGS_EINVAL, "rows/out NULL");
+    return llh_block_impl(c, 0, n_rows, rows, n_cols, cols, semantics, out);
+}
+
+int pwgs_llh_range(pwgs_ctx *c, int row0, int n_rows, int n_cols, const int32_t *cols, int semantics, double *out)
+{
+    return llh_block_impl(c, row0, n_rows, nullptr, n_cols, cols, semantics, out);
 }
 
 int pwgs_llh_rows(pwgs_ctx *c, int n_rows, const int32_t *rows, int semantics, double *out)
@@ -706,7 +902,7 @@ int pwgs_total_llh(pwgs_ctx *c, int semantics, double *out)
     if (semantics != PWGS_SEM_PY) return fail(PWGS_EINVAL, "unknown semantics");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(c->scratch.alloc((size_t)c->D + 1));
-    pair_llh_kernel<<<(c->D + 127) / 128, 128, 0, c->stream>>>(data_view(c), tree_view(c), 1, c->D, nullptr, 0, nullptr, 0, semantics,
+    pair_llh_kernel<<<(c->D + 127) / 128, 128, 0, c->stream>>>(data_view(c), tree_view(c), 1, 0, c->D, nullptr, 0, nullptr, 0, semantics,
                                                                kLogTinyMh, kLogTinyPy, kLogQuarter, c->scratch.p);
     CUDA_TRY(cudaGetLastError());
     sum_kernel<<<1, 1024, 0, c->stream>>>(c->D, c->scratch.p, c->scratch.p + c->D);
@@ -769,6 +965,9 @@ int pwgs_set_option(pwgs_ctx *c, const char *name, int64_t value)
     } else if (n == "mh_dist") {
         if (value < -1 || value > 1) return fail(PWGS_EINVAL, "mh_dist must be -1 (auto), 0 or 1");
         c->opt_dist = (int)value;
+    } else if (n == "mh_big") {
+        if (value < -1 || value > 1) return fail(PWGS_EINVAL, "mh_big must be -1 (auto), 0 or 1");
+        c->opt_big = (int)value;
     } else if (n == "mh_collapse") {
         c->opt_collapse = value != 0;
     } else if (n == "mh_stage") {
@@ -819,6 +1018,11 @@ int pwgs_get_option(pwgs_ctx *c, const char *name, int64_t *value)
     if (n == "mh_batch") *value = c->opt_batch;
     else if (n == "mh_ctas") *value = c->opt_ctas;
     else if (n == "n_sms") *value = c->n_sms;
+    else if (n == "grid_kernel_ns") {                     // device time of the last pwgs_llh_rows / _block / _range kernel
+        float ms = 0.f;
+        if (c->grid_timed) CUDA_TRY(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+        *value = (int64_t)(ms * 1e6);
+    }
     else if (n == "n_plain") *value = c->Dp;
     else if (n == "n_cnv_ssm") *value = c->M;
     else if (n == "launches") *value = c->n_launches;

@@ -44,6 +44,13 @@ __global__ void gather_node_kernel(int n, const int *__restrict__ idx, const int
     if (i < n) out[i] = node_of_datum[idx[i]];
 }
 
+// assignments of a few data changed (pwgs_move_data)
+__global__ void move_data_kernel(int n, const int *__restrict__ datum, const int *__restrict__ node, int *__restrict__ node_of_datum)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) node_of_datum[datum[i]] = node[i];
+}
+
 // ============================================================================ K0b
 // One thread per CNV-affected SSM m.  Pass 1 accumulates the tp=0 genome counts exactly like
 // compute_n_genomes(0) (params.py:120) to decide the substitutions of params.py:160-166; pass 2 writes the final
@@ -248,6 +255,25 @@ __host__ __device__ inline void cnv_state_sums(const DataView &dv, const TreeVie
 #pragma unroll
         for (int q = 0; q < 4; q++) { nr[q] += ph * (double)(cr[q] - pr[q]); nv[q] += ph * (double)(cv[q] - pv[q]); }
     }
+    // The callers DECIDE on these sums (a state with nv == 0 is dropped or substituted, nr + nv == 0 counts log 1e-99), and the
+    // signed deltas above can cancel to an exact 0 or a tiny negative where the reference's sum of non-negative terms is a tiny
+    // positive (and the other way round).  So whenever a sum a decision looks at is within rounding of zero, take all of them
+    // from the reference's own form, sum_k pi_k * coef_k: non-negative terms, zero exactly when every term is.  Rare (a node
+    // with pi ~ 0 carrying all of a state's variant copies), O(K) then.
+    bool near_zero = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) near_zero |= fabs(nv[q]) < 1e-7 || fabs(nr[q] + nv[q]) < 1e-7;
+    if (near_zero) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) { nr[q] = 0.0; nv[q] = 0.0; }
+        for (int k = 0; k < tv.K; k++) {
+            int cr[4], cv[4];
+            state_coefs(dv, tv, j, s, k, cr, cv);
+            const double p = tv.pi[k * T + tp];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { nr[q] += p * (double)cr[q]; nv[q] += p * (double)cv[q]; }
+        }
+    }
 }
 
 __host__ __device__ inline double datum_ll_at(const DataView &dv, const TreeView &tv, int j, int s, int semantics,
@@ -307,7 +333,7 @@ __host__ __device__ inline double datum_ll_at(const DataView &dv, const TreeView
 
 // mode 0: pairs (rows[r], cols[c]) -> out[r*n_cols + c]     (block of the datum x node grid; cols NULL = all K nodes)
 // mode 1: pairs (j, node_of_datum[j]) for all j -> out[j]    (terms of the complete-data likelihood)
-__global__ void pair_llh_kernel(DataView dv, TreeView tv, int mode, int n_rows, const int *__restrict__ rows, int n_cols,
+__global__ void pair_llh_kernel(DataView dv, TreeView tv, int mode, int row0, int n_rows, const int *__restrict__ rows, int n_cols,
                                 const int *__restrict__ cols, int col_major, int semantics, double log_tiny_mh, double log_tiny_py, double log_quarter,
                                 double *__restrict__ out)
 {
@@ -318,7 +344,8 @@ __global__ void pair_llh_kernel(DataView dv, TreeView tv, int mode, int n_rows, 
     if (mode == 0) {
         // row-major: out[r][c], neighbouring threads = neighbouring nodes; column-major: out[c][r], neighbouring threads = data
         const size_t r = col_major ? i % n_rows : i / n_cols;
-        j = rows[r]; s = (int)(col_major ? i / n_rows : i % n_cols);
+        j = rows ? rows[r] : row0 + (int)r;                      // rows == NULL: the range row0 .. row0 + n_rows - 1
+        s = (int)(col_major ? i / n_rows : i % n_cols);
         if (cols) s = cols[s];                                   // cols == NULL: all K nodes
     }
     else { j = (int)i; s = tv.node_of_datum[j]; }
@@ -380,7 +407,7 @@ static_assert(PWGS_MAX_BATCH / 32 <= MH_CWARPS, "the publish / read-totals steps
 #define MH_NARROW_BATCH 128              // batch cap while accepts are recent; the full cap (PWGS_MAX_BATCH) opens up after
 #define MH_WIDE_AFTER 8                  // this many all-reject batches in a row: an accept wastes the rest of its batch, so the wide
                                          // batch (half as many chain barriers per iteration) only pays at very low acceptance
-#define MH_DIST_MIN_CTAS 32              // chains with fewer CTAs draw every proposal locally in every CTA
+#define MH_DIST_MIN_CTAS 8               // chains with fewer CTAs draw every proposal locally in every CTA
 
 struct MhParams {
     int Dp, M, T, K;
@@ -411,6 +438,8 @@ struct MhParams {
     unsigned long long *counter;        // arrival counter of the chain's grid barrier (zeroed before launch)
     int *abort_flag;                    // watchdog: set when a spin wait exceeds MH_WATCHDOG_CYCLES; every CTA then leaves the loop
     double lbc_plain_sum, log_tiny;
+    double *gscratch;                   // mh_kernel<*, true> only: [cpc][gstride] the CTAs' state copies, proposal buffers and draw scratch in global
+    unsigned long long gstride;         // memory (trees whose node tables do not fit in shared memory), doubles per CTA
     unsigned long long *prof;           // optional [16 + cpc]: cycle counters of CTA 0 / thread 0, then every CTA's likelihood cycles (NULL = off)
 };
 
@@ -454,13 +483,19 @@ __host__ __device__ inline size_t mh_o_phi(int KT, int maxb) { return mh_even((s
 __host__ __device__ inline size_t mh_o_hast(int KT, int maxb) { return mh_o_phi(KT, maxb) + mh_phi_doubles(KT, maxb); }
 __host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return mh_even(mh_o_hast(K * T, maxb) + (size_t)maxb * T + maxb); }
 __host__ __device__ __forceinline__ int mh_phi_at(int b, int i, int KT) { return (b >> 2) * 4 * KT + i * 4 + (b & 3); }
-__host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb)
+// the part that grows with the tree: two state copies, two proposal buffers, the draw scratch of every warp.  Normally in shared
+// memory; mh_kernel<false, true> keeps it in global memory (p.gscratch), one region per CTA
+__host__ __device__ inline size_t mh_tree_doubles(int K, int T, int maxb)
 {
     size_t KT = (size_t)K * T;
-    const size_t red = MH_RED_DOUBLES(maxb);
-    return PWGS_LOG_TAB_DOUBLES + PWGS_EXP_TAB_DOUBLES + 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + red + maxb + 4 * (size_t)maxb +
-           2 * (size_t)K * (MH_CWARPS + 1);
+    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + 2 * (size_t)K * (MH_CWARPS + 1);
 }
+// the rest: tables of the logarithm / exponential, per-batch sums and totals
+__host__ __device__ inline size_t mh_fixed_doubles(int maxb)
+{
+    return PWGS_LOG_TAB_DOUBLES + PWGS_EXP_TAB_DOUBLES + MH_RED_DOUBLES(maxb) + maxb + 4 * (size_t)maxb;
+}
+__host__ __device__ inline size_t mh_smem_doubles(int K, int T, int maxb) { return mh_fixed_doubles(maxb) + mh_tree_doubles(K, T, maxb); }
 __host__ __device__ inline size_t mh_smem_ints(int K) { return CTL_WORDS + 2 * (size_t)K; }
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MH_CONSUMERS) : "memory"); }
@@ -965,7 +1000,7 @@ __device__ __noinline__ bool mh_epoch_start(const MhParams &p, const MhSmem &S, 
 // chain -- the first two batches after an accept by all warps of the chain (mh_epoch_start, one extra barrier), every later
 // batch by the producer warp of its owner CTA two batches ahead (mh_ring_tasks) -- and travels through a ring in global memory
 // under the chain barrier's release / acquire.  Chains with few CTAs draw locally in every CTA.
-template <bool STAGED>
+template <bool STAGED, bool BIG>
 __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ plist, int cpc)
 {
     double *sm = mh_sm;
@@ -979,14 +1014,19 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
 
     MhSmem S;
     {
+        // BIG: the tree-sized part lives in this CTA's region of p.gscratch (generic loads instead of LDS in the likelihood
+        // loops: several times slower, but any tree runs); a separate instantiation so that the normal kernel keeps its
+        // shared-memory addressing
         double *q = sm + PWGS_LOG_TAB_DOUBLES + PWGS_EXP_TAB_DOUBLES;
+        double *t = BIG ? p.gscratch + (size_t)rank * p.gstride : q;
         S.KT = KT; S.T = T; S.statestride = 4 * KT + 2 * T;
-        S.state0 = q; q += 2 * S.statestride;
+        S.state0 = t; t += 2 * S.statestride;
         S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = (int)mh_o_phi(KT, MAXB); S.o_hast = (int)mh_o_hast(KT, MAXB); S.o_logr = S.o_hast + MAXB * T;
-        S.buf0 = q; q += 2 * S.bufstride;
+        S.buf0 = t; t += 2 * S.bufstride;
+        S.pscratch = t; t += 2 * K * (MH_CWARPS + 1);
+        if (!BIG) q = t;
         S.red = q; q += MH_RED_DOUBLES(MAXB); S.llh = q; q += MAXB;
         S.seen = (unsigned long long *)q; q += 4 * MAXB;
-        S.pscratch = q; q += 2 * K * (MH_CWARPS + 1);
         S.ctl = (volatile int *)q; S.tin = (int *)q + CTL_WORDS; S.tout = S.tin + K;
     }
     pwgs_log_tab_fill(sm, tid, MH_THREADS);

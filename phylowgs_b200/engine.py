@@ -49,15 +49,28 @@ class Engine:
 
     # ------------------------------------------------------------------ tree
     def set_tree(self, parent, node_of_datum, phi, pi):
-        parent, nod = i32(parent), i32(node_of_datum)
+        """node_of_datum None: the device keeps the assignments it has (a tree that only grew, see pwgs_move_data)."""
+        parent = i32(parent)
+        nod = i32(node_of_datum) if node_of_datum is not None else None
         phi, pi = f64(phi), f64(pi)
         K = len(parent)
         if phi.shape != (K, self.T) or pi.shape != (K, self.T):
             raise ValueError("phi and pi must be [K, T]")
-        if nod.shape != (self.D,):
+        if nod is not None and nod.shape != (self.D,):
             raise ValueError("node_of_datum must have one entry per datum")
         check(_lib.load().pwgs_set_tree(self._h, K, p_i32(parent), p_i32(nod), p_f64(phi), p_f64(pi)))
         self.K = K
+
+    def move_data(self, datum, node):
+        datum, node = i32(np.atleast_1d(datum)), i32(np.atleast_1d(node))
+        check(_lib.load().pwgs_move_data(self._h, len(datum), p_i32(datum), p_i32(node)))
+
+    def host_buffer(self, shape):
+        """float64 array of `shape` in the context's page-locked buffer (valid until the next, larger request)."""
+        n = int(np.prod(shape))
+        ptr = C.c_void_p()
+        check(_lib.load().pwgs_host_buffer(self._h, max(8 * n, 8), C.byref(ptr)))
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(max(n, 1),))[:n].reshape(shape)
 
     # ------------------------------------------------------------------ MH
     def mh_run(self, iters, mh_std, seed=0, stream=0):
@@ -79,6 +92,16 @@ class Engine:
         check(_lib.load().pwgs_mh_wait(self._h, p_f64(phi), p_f64(pi), C.byref(ratio), C.byref(llh), C.byref(ms)))
         return dict(phi=phi, pi=pi, ratio=ratio.value, llh=llh.value, kernel_ms=ms.value)
 
+    @staticmethod
+    def mh_launch_multi(engines, iters, mh_std, seeds, streams):
+        """Several chains of one device in ONE cooperative launch (pwgs_mh_launch_multi); every engine then takes its own mh_wait()."""
+        n = len(engines)
+        hs = (C.c_void_p * n)(*[e._h for e in engines])
+        std = np.ascontiguousarray(np.broadcast_to(np.asarray(mh_std, dtype=np.float64), (n,)))
+        sd = (C.c_uint64 * n)(*[int(x) for x in np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (n,))])
+        st = (C.c_uint64 * n)(*[int(x) for x in np.broadcast_to(np.asarray(streams, dtype=np.uint64), (n,))])
+        check(_lib.load().pwgs_mh_launch_multi(n, hs, int(iters), p_f64(std), sd, st))
+
     # ------------------------------------------------------------------ likelihoods
     def llh_rows(self, rows, semantics=SEM_PY, col_major=False):
         """-> [n_rows, K]; col_major: [K, n_rows] (one contiguous column per node, PWGS_LAYOUT_COLS)."""
@@ -94,6 +117,19 @@ class Engine:
             return out
         check(_lib.load().pwgs_llh_block(self._h, len(rows), p_i32(rows), len(cols), p_i32(cols),
                                          int(semantics) | (LAYOUT_COLS if col_major else 0), p_f64(out)))
+        return out
+
+    def llh_range(self, row0, n_rows, cols=None, semantics=SEM_PY, col_major=False, out=None):
+        """llh_block for the data row0 .. row0 + n_rows - 1 (cols None: all nodes); `out`: where to write (e.g. host_buffer)."""
+        cols = i32(cols) if cols is not None else None
+        n_cols = len(cols) if cols is not None else self.K
+        shape = (n_cols, n_rows) if col_major else (n_rows, n_cols)
+        if out is None:
+            out = np.empty(shape)
+        assert out.shape == shape and out.flags.c_contiguous and out.dtype == np.float64
+        if out.size:
+            check(_lib.load().pwgs_llh_range(self._h, int(row0), int(n_rows), n_cols, p_i32(cols),
+                                             int(semantics) | (LAYOUT_COLS if col_major else 0), p_f64(out)))
         return out
 
     def total_llh(self, semantics=SEM_PY):

@@ -73,6 +73,30 @@ class Backend(object):
     def llh_block_t(self, rows, cols):
         return np.ascontiguousarray(self.llh_block(rows, cols).T)
 
+    # tree edits in the middle of a sweep; the defaults re-send everything through set_tree_arrays (what the CPU oracle behind
+    # this interface needs), the GPU backend sends only what changed
+    def grid_t(self, n_data, spare=0):
+        """[K + spare][n_data]: every datum in every node (start of a sweep) in the first K rows; the spare rows are storage for
+        the columns of nodes spawned during the sweep."""
+        g = self.llh_rows_t(np.arange(n_data, dtype=np.int32))
+        if spare:
+            full = np.empty((g.shape[0] + spare, n_data))
+            full[:g.shape[0]] = g
+            return full
+        return g
+
+    def update_tree_arrays(self, parent, node_of_datum, phi, pi):
+        """The tree grew (spawned nodes appended); node_of_datum is passed for backends that need everything again."""
+        self.set_tree_arrays(parent, node_of_datum, phi, pi)
+
+    def move_datum(self, n, k, parent, node_of_datum, phi, pi):
+        """Datum n moved to node k (node_of_datum already says so); the tree itself is unchanged since the last update."""
+        self.set_tree_arrays(parent, node_of_datum, phi, pi)
+
+    def llh_range_t(self, row0, n_data, cols):
+        """[len(cols)][n_data - row0]: the data still to be visited in the given nodes."""
+        return self.llh_block_t(np.arange(row0, n_data, dtype=np.int32), cols)
+
     # -- shared glue
     def sync_tree(self, tssb):
         nodes, parent, nod, phi, pi = flatten_tree(tssb)
@@ -114,6 +138,22 @@ class GpuBackend(Backend):
 
     def llh_block_t(self, rows, cols):
         return self.engine.llh_block(rows, cols, SEM_PY, col_major=True)
+
+    def grid_t(self, n_data, spare=0):
+        # straight into the context's page-locked buffer: 45 MB at 50k SSMs x 110 nodes arrive at PCIe speed (pageable: 10 ms)
+        K = self.engine.K
+        out = self.engine.host_buffer((K + spare, n_data))
+        self.engine.llh_range(0, n_data, None, SEM_PY, col_major=True, out=out[:K])
+        return out
+
+    def update_tree_arrays(self, parent, node_of_datum, phi, pi):
+        self.engine.set_tree(parent, None, phi, pi)
+
+    def move_datum(self, n, k, parent, node_of_datum, phi, pi):
+        self.engine.move_data(n, k)
+
+    def llh_range_t(self, row0, n_data, cols):
+        return self.engine.llh_range(row0, n_data - row0, cols, SEM_PY, col_major=True)
 
     def total_llh(self):
         return self.engine.total_llh(SEM_PY)

@@ -99,8 +99,10 @@ class _Grid(object):
         self._parent[:K], self._phi[:K], self._pi[:K] = parent, phi, pi
         self.spawned = getattr(t, "n_spawned", 0)
         self.calls = 1
-        self._full = b.llh_rows_t(np.arange(t.num_data, dtype=np.int32))     # [K][D]: the columns are views, no copies
-        self.cols = [self._full[k] for k in range(self._full.shape[0])]
+        # [K + spare][D]: the columns are views, no copies; the spare rows take the columns of nodes spawned during the sweep
+        # (fresh 400 KB arrays per spawned node cost more in page faults than the device call that fills them)
+        self._full = b.grid_t(t.num_data, spare=max(64, K // 2))
+        self.cols = [self._full[k] for k in range(K)]
         if not hasattr(t, "_ssms_of_cnv"):                  # CNV datum index -> SSM datum indices linked to it
             m = {}
             for d in t.data:
@@ -110,7 +112,7 @@ class _Grid(object):
 
     def _push_tree(self):
         K = len(self.nodes)
-        self.backend.set_tree_arrays(self._parent[:K], self.nod, self._phi[:K], self._pi[:K])
+        self.backend.update_tree_arrays(self._parent[:K], self.nod, self._phi[:K], self._pi[:K])
 
     def register(self, entry):
         """A node spawned during the sweep gets the next index."""
@@ -134,9 +136,10 @@ class _Grid(object):
         """Columns of nodes[first:] for the data still to be visited (rows n..)."""
         self._push_tree()
         cols = np.arange(first, len(self.nodes), dtype=np.int32)
-        block = self.backend.llh_block_t(np.arange(n, self.tssb.num_data, dtype=np.int32), cols)
+        block = self.backend.llh_range_t(n, self.tssb.num_data, cols)
         for i in range(len(cols)):
-            col = np.empty(self.tssb.num_data)
+            k = len(self.cols)
+            col = self._full[k] if k < self._full.shape[0] else np.empty(self.tssb.num_data)
             col[n:] = block[i]
             self.cols.append(col)
         self.spawned = getattr(self.tssb, "n_spawned", 0)
@@ -154,14 +157,15 @@ class _Grid(object):
         self.fetch_new_columns(n, first)
 
     def after_cnv_move(self, n, cnv_index):
+        K = len(self.nodes)
+        # (every spawn so far has been sent by fetch_new_columns; SSM moves change no other datum's likelihood)
+        self.backend.move_datum(cnv_index, int(self.nod[cnv_index]), self._parent[:K], self.nod, self._phi[:K], self._pi[:K])
         rows = self.tssb._ssms_of_cnv.get(cnv_index)
         if rows is None:
             return
         rows = rows[rows > n]
         if len(rows) == 0:
             return
-        self._push_tree()
-        K = len(self.nodes)
         block = self.backend.llh_block_t(rows, np.arange(K, dtype=np.int32))
         for k in range(K):
             self.cols[k][rows] = block[k]
@@ -250,7 +254,7 @@ def resample_assignments_native(tssb):
     import time
     timing = os.environ.get("PWGS_SWEEP_TIMING") == "1"
     t_start = time.perf_counter()
-    t_cb = [0.0, 0, 0]                                  # seconds inside callbacks, spawn events, CNV moves
+    t_cb = [0.0, 0, 0, 0.0]                             # seconds inside callbacks, spawn events, CNV moves, seconds mirroring spawns
     lib = _lib.load()
     grid = _Grid(tssb)
     t_grid = time.perf_counter()
@@ -296,6 +300,7 @@ def resample_assignments_native(tssb):
         try:
             first = len(grid.nodes)
             mirror_spawns()
+            t_cb[3] += time.perf_counter() - t0
             grid.fetch_new_columns(int(n), first)
             for k in range(first, len(grid.nodes)):
                 cols[k] = grid.cols[k].ctypes.data_as(_dp)
@@ -310,7 +315,7 @@ def resample_assignments_native(tssb):
     def on_cnv_move(_user, n):
         t0 = time.perf_counter()
         try:
-            grid.nod[:] = assign                            # the device needs the CNV's new node (and may as well get the rest)
+            grid.nod[n] = assign[n]                         # the device needs the CNV's new node (SSM moves change no likelihood)
             grid.after_cnv_move(int(n), int(n))
             return 0
         except BaseException as e:          # noqa: B902
@@ -366,8 +371,8 @@ def resample_assignments_native(tssb):
     if timing:
         t_end = time.perf_counter()
         sys.stderr.write("sweep timing: grid %.1f ms, setup %.1f ms, native sweep %.1f ms (of which callbacks %.1f ms: %d spawn events, "
-                         "%d CNV moves), mirror-back %.1f ms; K %d -> %d\n"
-                         % (1e3 * (t_grid - t_start), 1e3 * (t_setup - t_grid), 1e3 * (t_native - t_setup), 1e3 * t_cb[0], t_cb[1], t_cb[2],
+                         "%d CNV moves; %.1f ms of it creating the spawned nodes' Python twins), mirror-back %.1f ms; K %d -> %d\n"
+                         % (1e3 * (t_grid - t_start), 1e3 * (t_setup - t_grid), 1e3 * (t_native - t_setup), 1e3 * t_cb[0], t_cb[1], t_cb[2], 1e3 * t_cb[3],
                             1e3 * (t_end - t_native), K0, len(grid.nodes)))
 
 

@@ -7,7 +7,7 @@ for lib in "$@"; do
   echo "=== $tag"
   PWGS_LIB=$PWD/$lib timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
   for std in ${AB_STDS:-100}; do
-    PWGS_LIB=$PWD/$lib timeout 300 python bench.py --steps ${AB_STEPS:-10} --warmup 3 --no-cpu-baseline --profile-phases --mh-std $std ${AB_ARGS} \
+    PWGS_LIB=$PWD/$lib timeout 300 python bench.py --steps ${AB_STEPS:-10} --warmup 3 --no-cpu-baseline --no-accept-sweep --no-oracle-check --no-chain-sweep --no-grid --profile-phases --mh-std $std ${AB_ARGS} \
       2> gpurun_out/ab_${tag}_$std.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())

@@ -64,3 +64,26 @@ def test_deep_trees_many_links_and_zero_mass_nodes():
         for sem in (O.SEM_CPP, O.SEM_PY):
             want, got = O.llh_rows(data, t2, rows, sem), host_rows(data, t2, rows, sem)
             assert rel(got, want) < 1e-9, (seed, sem)
+
+
+@pytest.mark.parametrize("sem", [O.SEM_CPP, O.SEM_PY])
+@pytest.mark.parametrize("tiny", [1e-18, 3e-17, 1e-12, 0.0])
+def test_states_decided_on_sums_that_cancel(sem, tiny):
+    """the decisions "nv == 0" / "nv > 0" / "nr + nv > 0" (mh.hpp:100, params.py:160-166, data.py:52) were taken on the
+    sparse signed sums.  SSM 0 sits in node 1 (pi = tiny), its CNV below it in node 2 with copies (2, 0): state 1's variant
+    copies come from node 1 alone, nv1 = tiny * 1.  As phisub(1) - phisub(2) that is (0.5 + tiny) - 0.5 = 0 exactly for
+    tiny < 1 ulp -- the state would be dropped (Python) or substituted (C++) where the reference keeps it."""
+    T = 1
+    a = np.array([[30], [25], [900]], dtype=np.int32)
+    d = np.array([[60], [50], [1000]], dtype=np.int32)
+    mu_r, mu_v = np.array([0.999, 0.999, 0.999]), np.array([0.499, 0.499, 0.5])
+    data = O.Data(a, d, mu_r, mu_v, 2, np.array([0, 1, 1], dtype=np.int32), np.array([0], dtype=np.int32),
+                  np.array([2], dtype=np.int32), np.array([0], dtype=np.int32))
+    parent = np.array([-1, 0, 1], dtype=np.int32)
+    pi = np.array([[0.5 - tiny], [tiny], [0.5]])
+    phi = np.array([[1.0], [0.5 + tiny], [0.5]])
+    nod = np.array([1, 2, 2], dtype=np.int32)
+    tree = O.Tree(parent, nod, phi, pi)
+    rows = np.arange(3, dtype=np.int32)
+    want, got = O.llh_rows(data, tree, rows, sem), host_rows(data, tree, rows, sem)
+    assert rel(got, want) < 1e-9, (got, want)
