@@ -112,6 +112,9 @@ class Backend(object):
 
 
 class GpuBackend(Backend):
+    SCRATCH_COLS = 8
+    _scratch = None
+
     def __init__(self, data, device=0):
         arr = arrays_from_data(data)
         self.n_ssm = arr["n_ssm"]
@@ -123,6 +126,8 @@ class GpuBackend(Backend):
         import os
         if os.environ.get("PWGS_MH_COLLAPSE", "1") != "0" and self.engine.get_option("n_classes") > 0:
             self.engine.set_option("mh_collapse", 1)
+        if os.environ.get("PWGS_MH_BIG"):                   # tuning: -1 automatic, 1 / 0 force / forbid node tables in global memory
+            self.engine.set_option("mh_big", int(os.environ["PWGS_MH_BIG"]))
 
     def set_tree_arrays(self, parent, node_of_datum, phi, pi):
         self.engine.set_tree(parent, node_of_datum, phi, pi)
@@ -142,9 +147,10 @@ class GpuBackend(Backend):
     def grid_t(self, n_data, spare=0):
         # straight into the context's page-locked buffer: 45 MB at 50k SSMs x 110 nodes arrive at PCIe speed (pageable: 10 ms)
         K = self.engine.K
-        out = self.engine.host_buffer((K + spare, n_data))
+        out = self.engine.host_buffer((K + spare + self.SCRATCH_COLS, n_data))
         self.engine.llh_range(0, n_data, None, SEM_PY, col_major=True, out=out[:K])
-        return out
+        self._scratch = out[K + spare:].reshape(-1)         # page-locked landing area for the small blocks of the sweep
+        return out[:K + spare]
 
     def update_tree_arrays(self, parent, node_of_datum, phi, pi):
         self.engine.set_tree(parent, None, phi, pi)
@@ -153,7 +159,9 @@ class GpuBackend(Backend):
         self.engine.move_data(n, k)
 
     def llh_range_t(self, row0, n_data, cols):
-        return self.engine.llh_range(row0, n_data - row0, cols, SEM_PY, col_major=True)
+        n = (n_data - row0) * len(cols)
+        out = self._scratch[:n].reshape(len(cols), n_data - row0) if (self._scratch is not None and n <= len(self._scratch)) else None
+        return self.engine.llh_range(row0, n_data - row0, cols, SEM_PY, col_major=True, out=out)
 
     def total_llh(self):
         return self.engine.total_llh(SEM_PY)

@@ -167,8 +167,11 @@ class _Grid(object):
         if len(rows) == 0:
             return
         block = self.backend.llh_block_t(rows, np.arange(K, dtype=np.int32))
-        for k in range(K):
-            self.cols[k][rows] = block[k]
+        if K <= self._full.shape[0]:                        # every column is a row of the sweep's buffer: one scatter
+            self._full[:K, rows] = block
+        else:
+            for k in range(K):
+                self.cols[k][rows] = block[k]
         self.calls += 1
 
     def get(self, n, node):
