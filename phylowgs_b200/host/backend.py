@@ -147,7 +147,11 @@ class GpuBackend(Backend):
     def grid_t(self, n_data, spare=0):
         # straight into the context's page-locked buffer: 45 MB at 50k SSMs x 110 nodes arrive at PCIe speed (pageable: 10 ms)
         K = self.engine.K
-        out = self.engine.host_buffer((K + spare + self.SCRATCH_COLS, n_data))
+        rows = K + spare + self.SCRATCH_COLS
+        # page-locking costs ~1 ms per MB: ask once for what the trees of a burn-in need (a few hundred nodes) while that stays
+        # under 256 MB, so that a growing tree does not pay it again sweep after sweep
+        floor_rows = min(384, (256 << 20) // (8 * max(n_data, 1)))
+        out = self.engine.host_buffer((max(rows, floor_rows), n_data))[:rows]
         self.engine.llh_range(0, n_data, None, SEM_PY, col_major=True, out=out[:K])
         self._scratch = out[K + spare:].reshape(-1)         # page-locked landing area for the small blocks of the sweep
         return out[:K + spare]

@@ -17,10 +17,10 @@ for K in (11, 40, 120):
         for k in range(K - 1, 0, -1): phi[parent[k]] += phi[k]
         nod = rng.integers(1, K, size=D).astype(np.int32)
     t0 = time.perf_counter(); eng.set_tree(parent, nod, phi, pi); t1 = time.perf_counter()
-    rows = np.arange(D, dtype=np.int32)
-    eng.llh_rows(rows, 1)
+    buf = eng.host_buffer((K, D))                    # the sweep's form: column-major, into page-locked memory
+    eng.llh_range(0, D, None, 1, col_major=True, out=buf)
     ts = []
     for _ in range(3):
-        t = time.perf_counter(); g = eng.llh_rows(rows, 1); ts.append(time.perf_counter() - t)
+        t = time.perf_counter(); g = eng.llh_range(0, D, None, 1, col_major=True, out=buf); ts.append(time.perf_counter() - t)
     t = time.perf_counter(); tot = eng.total_llh(1); t2 = time.perf_counter() - t
-    print("K=%3d: set_tree %.2f ms, grid D x K = %d x %d: %.2f ms (%.1f MB out), total_llh %.2f ms" % (K, 1e3*(t1-t0), D, K, 1e3*min(ts), g.nbytes/1e6, 1e3*t2))
+    print("K=%3d: set_tree %.2f ms, grid D x K = %d x %d: %.2f ms end to end, kernel %.3f ms (%.1f MB out), total_llh %.2f ms" % (K, 1e3*(t1-t0), D, K, 1e3*min(ts), eng.get_option("grid_kernel_ns") * 1e-6, g.nbytes/1e6, 1e3*t2))

@@ -4,7 +4,7 @@ import csv
 import subprocess
 import sys
 
-KEEP = ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "launch__block_size", "launch__grid_size",
+KEEP = ("dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct", "smsp__thread_inst_executed_per_inst_executed", "sm__warps_active.avg.pct", "gpu__time_duration.sum", "launch__block_size", "launch__grid_size",
         "launch__registers_per_thread", "launch__shared_mem", "sm__cycles_elapsed.avg", "sm__inst_executed.sum.p",
         "sm__inst_executed_pipe_fp64", "sm__inst_executed_pipe_xu.avg", "sm__pipe_fp64_cycles_active.avg", "sm__issue_active.avg",
         "sm__warps_active.avg.per_cycle_active", "smsp__average_warps_issue_stalled", "smsp__issue_active.avg", "smsp__warps_eligible.avg",
@@ -15,7 +15,7 @@ rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 for r in rows[2:]:
     d = dict(zip(hdr, r))
-    if "mh_kernel" not in d.get("Kernel Name", ""):
+    if (sys.argv[2] if len(sys.argv) > 2 else "mh_kernel") not in d.get("Kernel Name", ""):
         continue
     print("%-103s %s" % ("Kernel Name", d["Kernel Name"]))
     for k, u in sorted(zip(hdr, units)):
