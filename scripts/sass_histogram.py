@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "phylowgs_b200", "libpwgs_b200.so")
+LIB = os.environ.get("PWGS_LIB") or os.path.join(ROOT, "phylowgs_b200", "libpwgs_b200.so")
 FP64 = ("DFMA", "DADD", "DMUL", "DSETP", "DMNMX")
 
 
