@@ -92,9 +92,15 @@ class Node(object):
     # -- data bookkeeping
     def add_datum(self, n):
         self.data.add(n)
+        t = self.tssb
+        if t is not None:                                   # invalidates the cached assignment array of backend.flatten_tree
+            t._assign_version = getattr(t, "_assign_version", 0) + 1
 
     def remove_datum(self, n):
         self.data.remove(n)
+        t = self.tssb
+        if t is not None:
+            t._assign_version = getattr(t, "_assign_version", 0) + 1
 
     def num_local_data(self):
         return len(self.data)
@@ -205,7 +211,7 @@ class TSSB(object):
     # the generator and the device context are process-local: keep them out of trees.zip / state pickles
     def __getstate__(self):
         st = dict(self.__dict__)
-        for key in ("backend", "rng", "ustream", "_ssms_of_cnv", "_tree_pickler"):
+        for key in ("backend", "rng", "ustream", "_ssms_of_cnv", "_tree_pickler", "_nod_cache", "_assign_version"):
             st.pop(key, None)
         return st
 

@@ -88,7 +88,7 @@ class _Grid(object):
             self.entries.append(e)
             stack.extend(reversed(e["children"]))
         assert all(e["node"] is nd for e, nd in zip(self.entries, self.nodes))
-        self.nod = nod
+        self.nod = nod.copy()                             # the sweep edits it; flatten_tree keeps its own for the cache
         # the tree as arrays, kept in step with the spawns of the sweep (rows appended; a spawn also changes its parent's pi):
         # re-reading every node object at each of the ~100 refreshes of a sweep cost more than the refreshes themselves
         K = len(self.nodes)
@@ -370,6 +370,8 @@ def resample_assignments_native(tssb):
             nd = nodes[k]
             assignments[n] = nd
             data[n].node = nd
+    # the assignments as an array, for the next flatten_tree (the set operations above went around Node.add_datum)
+    tssb.__dict__["_nod_cache"] = (getattr(tssb, "_assign_version", 0), list(grid.nodes), assign.copy())
     tssb.last_grid_refreshes = grid.calls
     if timing:
         t_end = time.perf_counter()
