@@ -254,6 +254,7 @@ def tree_sample_rate(s, device, iterations=6, cpu_mh=None, cpu_seconds=10.0):
         O.write_ssm_cnv(data, ssm, cnv)
         codes, n_ssms, n_cnvs, _ = E.load_data(ssm, cnv)
     E.install_pickle_aliases()
+    E.tune_allocator()                                 # as evolve.do_mcmc does
     rng = np.random.RandomState(1)
     backend = GpuBackend(codes, device=device)
     root = alleles(conc=0.1, ntps=len(codes[0].a))

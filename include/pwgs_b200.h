@@ -190,6 +190,14 @@ typedef struct pwgs_sweep {
 } pwgs_sweep;
 int pwgs_resample_assignments(pwgs_sweep *sweep);
 
+/* Host code, no device: byte assembly of the data list of a tree pickle (evolve.py:233 pickles the whole TSSB with all its
+ * Datum objects for trees.zip, util2.py:250-262; host/fastpickle.py keeps one constant byte fragment per datum).  Writes, for
+ * i = 0..n-1:  frags[frag_off[i] .. frag_off[i+1])  |  reference ref_of[i]  |  tail.   refs is a table of 8-byte records
+ * {length <= 7, opcode bytes}; ref_of[i] < 0 writes the fragment alone.  Returns the number of bytes written (<= cap), or a
+ * negative PWGS_E* code (PWGS_ELIMIT: cap too small). */
+int64_t pwgs_pickle_join(int32_t n, const uint8_t *frags, const int64_t *frag_off, const int32_t *ref_of, int32_t n_refs,
+                         const uint8_t *refs, const uint8_t *tail, int32_t tail_len, uint8_t *out, int64_t cap);
+
 /* Diagnostics: the MH kernel's branch-free fp64 routines on caller-supplied arguments x[n] (positive, normal):
  * out[0..n) = log(x), out[n..2n) = exp(-x), out[2n..3n) = x / (1 + x).  Used by the accuracy test. */
 int pwgs_math_selftest(int device, int n, const double *x, double *out);

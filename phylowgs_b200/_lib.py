@@ -40,6 +40,8 @@ SIGNATURES = {
     "pwgs_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "pwgs_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "pwgs_resample_assignments": (C.c_int, [C.c_void_p]),      # struct pwgs_sweep*, see host/sampler.py::_Sweep
+    "pwgs_pickle_join": (C.c_int64, [C.c_int32, C.c_void_p, C.c_void_p, _i32p, C.c_int32, C.c_void_p, C.c_char_p, C.c_int32,
+                                     C.c_void_p, C.c_int64]),
     "pwgs_math_selftest": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p]),
     "pwgs_fp64_peak": (C.c_int, [C.c_int, _f64p]),
     "pwgs_selftest_llh_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _f64p, _i32p, _i32p, _i32p, _i32p,

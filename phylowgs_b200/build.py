@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpwgs_b200.so")
-SOURCES = ["pwgs_api.cu", "pwgs_host_sampler.cpp"]
-DEPS = ["pwgs_api.cu", "pwgs_host_sampler.cpp", "pwgs_kernels.cuh", "pwgs_device.cuh", os.path.join("..", "..", "include", "pwgs_b200.h")]
+SOURCES = ["pwgs_api.cu", "pwgs_host_sampler.cpp", "pwgs_host_pickle.cpp"]
+DEPS = ["pwgs_api.cu", "pwgs_host_sampler.cpp", "pwgs_host_pickle.cpp", "pwgs_kernels.cuh", "pwgs_device.cuh", os.path.join("..", "..", "include", "pwgs_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
 

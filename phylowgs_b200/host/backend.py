@@ -31,14 +31,12 @@ def arrays_from_data(data):
                 cnv_c1=np.array(c1, dtype=np.int32), cnv_c2=np.array(c2, dtype=np.int32))
 
 
-def flatten_tree(tssb):
-    """Preorder node list (get_mixture order = the ids evolve.py:175-177 assigns) -> (nodes, parent, node_of_datum, phi, pi).
-    node_of_datum is rebuilt from the nodes' data sets only when an assignment changed since the last call (Node.add_datum /
-    remove_datum bump tssb._assign_version; the native sweep stores what it knows): otherwise the cached array is re-indexed to
-    the current node order -- the tree is flattened three times per MCMC iteration and the rebuild was most of each."""
-    _, nodes = tssb.get_mixture()
+def assignment_array(tssb, nodes):
+    """node_of_datum (index into `nodes`) as an int32 array, or None when a datum sits in a node that is not in `nodes`.
+    Rebuilt from the nodes' data sets only when an assignment changed since the last call (Node.add_datum / remove_datum bump
+    tssb._assign_version; the native sweep stores what it knows): otherwise the cached array is re-indexed to the given node
+    order."""
     pos = {id(nd): k for k, nd in enumerate(nodes)}
-    parent = np.array([-1 if nd.parent() is None else pos[id(nd.parent())] for nd in nodes], dtype=np.int32)
     nod = None
     cache = tssb.__dict__.get("_nod_cache")
     if cache is not None and cache[0] == getattr(tssb, "_assign_version", 0) and len(cache[2]) == tssb.num_data:
@@ -48,11 +46,25 @@ def flatten_tree(tssb):
         if cand.min() >= 0 and np.array_equal(np.bincount(cand, minlength=len(nodes)), [len(nd.data) for nd in nodes]):
             nod = cand
     if nod is None:
-        nod = np.zeros(tssb.num_data, dtype=np.int32)
+        nod = np.full(tssb.num_data, -1, dtype=np.int32)
         for k, nd in enumerate(nodes):
             if nd.data:
                 nod[np.fromiter(nd.data, dtype=np.int64, count=len(nd.data))] = k
+        if tssb.num_data and nod.min() < 0:
+            return None
     tssb.__dict__["_nod_cache"] = (getattr(tssb, "_assign_version", 0), nodes, nod)
+    return nod
+
+
+def flatten_tree(tssb):
+    """Preorder node list (get_mixture order = the ids evolve.py:175-177 assigns) -> (nodes, parent, node_of_datum, phi, pi).
+    The tree is flattened three times per MCMC iteration; node_of_datum comes from `assignment_array`'s cache."""
+    _, nodes = tssb.get_mixture()
+    pos = {id(nd): k for k, nd in enumerate(nodes)}
+    parent = np.array([-1 if nd.parent() is None else pos[id(nd.parent())] for nd in nodes], dtype=np.int32)
+    nod = assignment_array(tssb, nodes)
+    if nod is None:
+        raise ValueError("a datum is assigned to a node outside the tree")
     phi = np.array([np.asarray(nd.params, dtype=np.float64).reshape(-1) for nd in nodes])
     pi = np.array([np.asarray(nd.pi, dtype=np.float64).reshape(-1) for nd in nodes])
     return nodes, parent, nod, phi, pi

@@ -19,6 +19,11 @@ reference to the datum's node.  So the tree is pickled in two parts:
     the ordinary pickler's (a tree with more memo entries than that falls back).  Datums that other datums point to (the CNVs of an SSM's `cnv` list) are defined in a preamble
     (`... POP`) so that every reference follows its definition.
 
+The join of the ~3 D byte strings of the second part is done by host code of the library (pwgs_pickle_join,
+csrc/pwgs_host_pickle.cpp) from the assignment array the sweeps maintain (backend.assignment_array) straight into the result,
+which is then a `bytearray` (what zipfile.writestr and pickle.loads take as they take bytes); the Python join remains for
+trees the shortcut does not cover and is byte-identical (tests/test_fastpickle.py).
+
 The result unpickles (plain `pickle.load`) to the same object graph: same attributes, `datum.node` the very node
 object of `tssb.assignments`, `datum.tssb` the tree, `cnv` links pointing at the CNV datums of the same list.  Anything
 unexpected (an attribute that is not a plain value, a reference cycle between datums) falls back to the ordinary pickler."""
@@ -65,7 +70,7 @@ def compat_pickler(buf):
 
 def compat_finish(stream):
     assert stream[:2] == b"\x80\x02"
-    return stream[:2] + _NP_PREAMBLE + stream[2:]
+    return b"".join([stream[:2], _NP_PREAMBLE, stream[2:]])
 
 
 def compat_dumps(obj):
@@ -127,6 +132,7 @@ class TreePickler(object):
             self._key("tssb")
             self.frags = frags
             self.referenced = sorted(referenced)
+            self._native_cache()
         except (ValueError, KeyError, TypeError, AttributeError):
             self.ok = False
 
@@ -157,6 +163,60 @@ class TreePickler(object):
                 raise ValueError("attribute %s of a datum is not a plain value" % key)
         parts.append(self._key("node"))
         return b"".join(parts)
+
+    def _native_cache(self):
+        """The list part as one byte string + offsets for pwgs_pickle_join (csrc/pwgs_host_pickle.cpp): the fragment of every
+        datum, a back-reference for those the preamble has already defined."""
+        import numpy as np
+        parts = list(self.frags)
+        for j in self.referenced:
+            parts[j] = _get(_BASE + 1 + j)
+        self.blob = b"".join(parts)
+        self.off = np.zeros(len(parts) + 1, dtype=np.int64)
+        np.cumsum([len(p) for p in parts], out=self.off[1:])
+        self.standalone = np.array(self.referenced, dtype=np.int64)
+
+    def _join_native(self, tssb, memo, tail, prefix, suffix):
+        """prefix + b"".join of [fragment, node reference, tail] over the data + suffix as one bytearray, the join done by the
+        library's host code straight into the result; None when the shortcut does not apply (the caller then joins in Python)."""
+        import ctypes as C
+        import numpy as np
+        from .. import _lib
+        from .backend import assignment_array
+        try:
+            lib = _lib.load()
+        except _lib.PwgsError:
+            return None
+        data, assignments = self.data, tssb.assignments
+        n = len(data)
+        if len(assignments) != n or any(data[i].node is not assignments[i] for i in {0, n // 2, n - 1}):
+            return None                                  # datum.node is what the format stores; it must be the assignment
+        nodes = tssb.get_nodes()
+        if any(id(nd) not in memo for nd in nodes):
+            return None
+        nod = assignment_array(tssb, nodes)
+        if nod is None:
+            return None
+        refs = np.zeros((len(nodes), 8), dtype=np.uint8)
+        for k, nd in enumerate(nodes):
+            r = _get(memo[id(nd)][0])
+            refs[k, 0] = len(r)
+            refs[k, 1:1 + len(r)] = np.frombuffer(r, dtype=np.uint8)
+        ref_of = np.ascontiguousarray(nod, dtype=np.int32)
+        if len(self.standalone):
+            ref_of = ref_of.copy()
+            ref_of[self.standalone] = -1
+        p0 = len(prefix)
+        cap = len(self.blob) + n * (5 + len(tail))
+        out = bytearray(p0 + cap + len(suffix))
+        out[:p0] = prefix
+        w = lib.pwgs_pickle_join(n, self.blob, self.off.ctypes.data, ref_of.ctypes.data_as(C.POINTER(C.c_int32)), len(nodes),
+                                 refs.ctypes.data, tail, len(tail), C.byref((C.c_char * len(out)).from_buffer(out), p0), cap)
+        if w < 0:
+            return None
+        out[p0 + w:p0 + w + len(suffix)] = suffix
+        del out[p0 + w + len(suffix):]
+        return out
 
     def _fresh(self):
         """The cache assumes the datums' own attributes never change; spot-check a few."""
@@ -191,7 +251,7 @@ class TreePickler(object):
             pk.dump(root)
         finally:
             tssb.__dict__ = saved
-        main = compat_finish(buf.getvalue())
+        main = compat_finish(buf.getbuffer())
         memo = pk.memo.copy()                            # id(obj) -> (index, obj)
         marker = _plain(_PLACEHOLDER)
         at = main.find(marker)
@@ -209,16 +269,24 @@ class TreePickler(object):
         for name, idx in self.keys.items():
             out += [_plain(name), _put(idx), _POP]
         frags = self.frags
+        view = memoryview(main)
+        try:
+            for j in self.referenced:                    # define the linked-to datums first
+                nd = data[j].node
+                out += [frags[j], _NONE if nd is None else _get(memo[id(nd)][0]), tail, _POP]
+        except (KeyError, AttributeError):               # a datum's node is not part of the tree
+            return compat_dumps(root)
+        out += [_EMPTY_LIST, _MARK]
+        whole = self._join_native(tssb, memo, tail, b"".join([view[:at]] + out), b"".join([_APPENDS, view[end:]]))
+        if whole is not None:
+            return whole
         noderef = {id(None): _NONE}
         for oid, (idx, obj) in memo.items():
             noderef[oid] = _get(idx)
         try:
-            refs = [noderef[id(d.node)] for d in data]   # KeyError: a datum's node is not part of the tree
+            refs = [noderef[id(d.node)] for d in data]
         except (KeyError, AttributeError):
             return compat_dumps(root)
-        for j in self.referenced:                        # define the linked-to datums first
-            out += [frags[j], refs[j], tail, _POP]
-        out += [_EMPTY_LIST, _MARK]
         n = len(data)
         body = [tail] * (3 * n)
         body[0::3] = frags
@@ -227,7 +295,7 @@ class TreePickler(object):
             body[3 * j], body[3 * j + 1], body[3 * j + 2] = _get(_BASE + 1 + j), b"", b""
         out += body
         out.append(_APPENDS)
-        return main[:at] + b"".join(out) + main[end:]
+        return b"".join([view[:at]] + out + [view[end:]])       # one allocation, one copy of every part
 
 
 def dumps(tssb, root=None):

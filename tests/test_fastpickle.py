@@ -100,6 +100,34 @@ def test_fast_pickle_follows_the_chain_and_only_uses_protocol_2_opcodes():
     assert ops <= proto2, ops - proto2
 
 
+def test_native_join_writes_the_bytes_of_the_python_join():
+    """pwgs_pickle_join (host code of the library) against the Python join of the same fragments, through tree edits."""
+    t = make_tree(n_children=4, seed=5)
+    nodes = t.get_nodes()
+    E.map_datum_to_node(t)
+    for step in range(3):
+        for n in range(step, t.num_data, 2):
+            old, new = t.assignments[n], nodes[1 + (n + 2 * step) % (len(nodes) - 1)]
+            old.remove_datum(n)
+            new.add_datum(n)
+            t.assignments[n] = new
+            t.data[n].node = new
+        native = fastpickle.dumps(t)
+        tp = t.__dict__["_tree_pickler"]
+        assert tp.ok and isinstance(native, bytearray)                      # the native join ran
+        tp._join_native = lambda *a: None
+        try:
+            python = fastpickle.dumps(t)
+        finally:
+            del tp._join_native
+        assert isinstance(python, bytes) and python == native
+    t.data[0].node = nodes[0]                                               # datum.node out of step with the assignments:
+    blob = fastpickle.dumps(t)
+    assert isinstance(blob, bytes)                                          # the shortcut steps aside
+    got = pickle.loads(blob)
+    assert got.data[0].node is got.root["node"] and got.assignments[0] is not got.root["node"]
+
+
 def test_fast_pickle_without_cnvs_and_with_unassigned_nodes(tmp_path):
     empty = str(tmp_path / "empty_cnv.txt")
     open(empty, "w").close()
