@@ -274,6 +274,8 @@ def tree_sample_rate(s, device, iterations=6, cpu_mh=None, cpu_seconds=10.0):
         t = [time.perf_counter()]
         tssb.resample_assignments(); t.append(time.perf_counter())
         tssb.cull_tree()
+        if it == 0:
+            E.map_datum_to_node(tssb)                  # evolve.do_mcmc: once per run, the sweeps keep datum.node in step afterwards
         acc = float(metropolis(tssb, MH_ITR, mh_std, 0, n_ssms, n_cnvs, "", "", 1, 1, ".", stream=it)); t.append(time.perf_counter())
         if acc < 0.08 and mh_std < 10000:
             mh_std *= 2.0

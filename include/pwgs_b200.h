@@ -122,6 +122,11 @@ int pwgs_llh_rows(pwgs_ctx *ctx, int n_rows, const int32_t *rows, int semantics,
 int pwgs_llh_block(pwgs_ctx *ctx, int n_rows, const int32_t *rows, int n_cols, const int32_t *cols, int semantics, double *out);
 /* The same for the data row0 .. row0 + n_rows - 1 (the data an assignment sweep has still to visit): no row list to send. */
 int pwgs_llh_range(pwgs_ctx *ctx, int row0, int n_rows, int n_cols, const int32_t *cols, int semantics, double *out);
+/* The same, column-major (PWGS_LAYOUT_COLS required), written in place into a wider array: node cols[c] of datum row0 + r lands at
+ * out[c * out_pitch + r] (out_pitch >= n_rows, in doubles) -- the columns of newly spawned nodes go straight into the sweep's
+ * [node][datum] grid with one strided DMA. */
+int pwgs_llh_range_pitched(pwgs_ctx *ctx, int row0, int n_rows, int n_cols, const int32_t *cols, int semantics, double *out,
+                           int64_t out_pitch);
 
 /* semantics MH: multi_param_post of the current state (mh.cpp:147-166).
  * semantics PY: the data term of TSSB.complete_data_log_likelihood (tssb.py:404-410, alleles.py:55-56). */
@@ -164,7 +169,15 @@ int pwgs_get_stream(pwgs_ctx *ctx, void **stream);
  *   read: the callee mirrors spawn_*[already mirrored .. n_spawned) and stores the new nodes' columns in cols[].
  *   on_cnv_move(user, n): CNV datum n moved (assignments[n] is already updated): refresh the rows of its SSMs that are still
  *   to be visited.
- * Returns 0, or a negative code (PWGS_EINVAL; -3 uniforms exhausted; -4 node / spawn capacity; -6/-7 callback failure). */
+ *   With ctx != NULL and on_spawn == on_cnv_move == NULL the library refreshes the grid itself, with no trip through the
+ *   caller's language per tree edit (a sweep at 50k SSMs has ~100 of them): a spawn event appends the new nodes to the tables
+ *   below (child pi = frac * parent pi, parent pi -= child pi, child phi = child pi: alleles.py:35-37), sends the grown tree
+ *   (pwgs_set_tree with NULL assignments) and fills the new nodes' columns for the data still to come (rows n.. of
+ *   cols[k] = grid + k * n_data for k < cap_cols, library-owned memory beyond); a CNV move is one pwgs_move_data plus the rows of
+ *   the CNV's SSMs still to come (ssm_ptr / ssm_idx, ascending) in all nodes.  The context must hold the sweep's tree, in the
+ *   sweep's node order, and its assignments.  n_refreshes counts the device round trips.
+ * Returns 0, or a negative code (PWGS_EINVAL; -3 uniforms exhausted; -4 node / spawn capacity; -6/-7 callback failure;
+ * -8 device refresh failed, see pwgs_last_error). */
 typedef struct pwgs_sweep {
     int32_t n_data, n_ssm;
     int32_t n_nodes, cap_nodes;
@@ -187,6 +200,16 @@ typedef struct pwgs_sweep {
     int (*on_cnv_move)(void *user, int32_t n);
     int (*refill)(void *user);
     int32_t n_moved, n_shrunk, uniforms_used;   /* out */
+    /* library-side refreshes (see above); all unused when the callbacks are given */
+    pwgs_ctx *ctx;
+    int32_t ntps, cap_cols;
+    int32_t *tree_parent;             /* [cap_nodes] in/out: parent of every node incl. the spawned ones */
+    double *phi, *pi;                 /* [cap_nodes][ntps] in/out */
+    double *grid;                     /* [cap_cols][n_data], ideally inside pwgs_host_buffer (page-locked) */
+    const int32_t *ssm_ptr, *ssm_idx; /* CSR over the CNV data: SSMs linked to CNV datum n_ssm + j, ascending */
+    double *scratch;                  /* landing area for the row blocks of a CNV move (page-locked if possible), or NULL */
+    int64_t scratch_len;              /* doubles */
+    int32_t n_refreshes;              /* out */
 } pwgs_sweep;
 int pwgs_resample_assignments(pwgs_sweep *sweep);
 

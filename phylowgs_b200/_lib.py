@@ -31,6 +31,7 @@ SIGNATURES = {
     "pwgs_llh_rows": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, _f64p]),
     "pwgs_llh_block": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int, _i32p, C.c_int, _f64p]),
     "pwgs_llh_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _f64p]),
+    "pwgs_llh_range_pitched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _f64p, C.c_int64]),
     "pwgs_move_data": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p]),
     "pwgs_host_buffer": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "pwgs_total_llh": (C.c_int, [C.c_void_p, C.c_int, _f64p]),

@@ -836,7 +836,8 @@ int pwgs_mh_run(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint64_t s
 }
 
 // ------------------------------------------------------------------ likelihood grid / totals
-static int llh_block_impl(pwgs_ctx *c, int row0, int n_rows, const int32_t *rows, int n_cols, const int32_t *cols, int semantics, double *out)
+static int llh_block_impl(pwgs_ctx *c, int row0, int n_rows, const int32_t *rows, int n_cols, const int32_t *cols, int semantics, double *out,
+                          int64_t out_pitch = 0)
 {
     if (!c) return fail(PWGS_EINVAL, "ctx is NULL");
     if (!c->tree_set) return fail(PWGS_ESTATE, "pwgs_set_tree must be called first");
@@ -871,7 +872,12 @@ static int llh_block_impl(pwgs_ctx *c, int row0, int n_rows, const int32_t *rows
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev3, c->stream));
     c->n_launches++;
-    CUDA_TRY(cudaMemcpyAsync(out, c->scratch.p, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (out_pitch > 0) {                                   // column-major block into the columns of a wider host array
+        if (!col_major || out_pitch < n_rows) return fail(PWGS_EINVAL, "a pitched output needs PWGS_LAYOUT_COLS and pitch >= n_rows");
+        CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)out_pitch * sizeof(double), c->scratch.p, (size_t)n_rows * sizeof(double),
+                                   (size_t)n_rows * sizeof(double), (size_t)n_cols, cudaMemcpyDeviceToHost, c->stream));
+    } else
+        CUDA_TRY(cudaMemcpyAsync(out, c->scratch.p, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->grid_timed = true;
     return PWGS_OK;
@@ -886,6 +892,12 @@ int pwgs_llh_block(pwgs_ctx *c, int n_rows, const int32_t *rows, int n_cols, con
 int pwgs_llh_range(pwgs_ctx *c, int row0, int n_rows, int n_cols, const int32_t *cols, int semantics, double *out)
 {
     return llh_block_impl(c, row0, n_rows, nullptr, n_cols, cols, semantics, out);
+}
+
+int pwgs_llh_range_pitched(pwgs_ctx *c, int row0, int n_rows, int n_cols, const int32_t *cols, int semantics, double *out, int64_t out_pitch)
+{
+    if (out_pitch <= 0) return fail(PWGS_EINVAL, "out_pitch must be positive");
+    return llh_block_impl(c, row0, n_rows, nullptr, n_cols, cols, semantics, out, out_pitch);
 }
 
 int pwgs_llh_rows(pwgs_ctx *c, int n_rows, const int32_t *rows, int semantics, double *out)

@@ -10,6 +10,8 @@
 #include "../../include/pwgs_b200.h"
 #include <cmath>
 #include <cfloat>
+#include <cstring>
+#include <memory>
 #include <vector>
 
 namespace {
@@ -19,6 +21,10 @@ struct Tree {
     std::vector<double> main;
     std::vector<std::vector<int>> kids;
     std::vector<std::vector<double>> sticks;
+    // right edges of the children's intervals, 1 - prod(1 - stick), kept as the running product tssb.py:349-352 recomputes at
+    // every visit (same operations in the same order, so the same bits)
+    std::vector<std::vector<double>> edges;
+    std::vector<double> rem;
 };
 
 struct Sampler {
@@ -54,8 +60,12 @@ struct Sampler {
         t.main.push_back(mn);
         t.kids.emplace_back();
         t.sticks.emplace_back();
+        t.edges.emplace_back();
+        t.rem.push_back(1.0);
         t.kids[node].push_back(id);
         t.sticks[node].push_back(stick);
+        t.rem[node] *= 1.0 - stick;
+        t.edges[node].push_back(1.0 - t.rem[node]);
         const int k = s->n_spawned++;
         s->spawn_parent[k] = node; s->spawn_stick[k] = stick; s->spawn_main[k] = mn; s->spawn_frac[k] = frac;
     }
@@ -65,22 +75,17 @@ struct Sampler {
     {
         int node = 0, depth = 0;
         path.clear();
-        std::vector<double> edges;
         for (;;) {
             const double mn = t.main[node];
             if (depth >= s->max_depth || u < mn) return node;
             u = (u - mn) / (1.0 - mn);
             int index = 0;
             if (depth > 0) {
-                double rem = 1.0;
-                edges.clear();
-                for (double st : t.sticks[node]) { rem *= 1.0 - st; edges.push_back(1.0 - rem); }
-                while (edges.empty() || edges.back() < u) {
+                while (t.edges[node].empty() || t.edges[node].back() < u) {
                     spawn_child(node);
                     if (err) return node;
-                    rem *= 1.0 - t.sticks[node].back();
-                    edges.push_back(1.0 - rem);
                 }
+                const std::vector<double> &edges = t.edges[node];
                 while (edges[index] < u) index++;
                 const double left = index ? edges[index - 1] : 0.0;
                 u = (u - left) / (edges[index] - left);
@@ -111,10 +116,75 @@ struct Sampler {
         return cand.size() > cur.size() ? 1 : (cand.size() < cur.size() ? -1 : 0);
     }
 
+    // ---- library-side refreshes of the grid (s->ctx given, no callbacks)
+    std::vector<std::unique_ptr<double[]>> own_cols;                  // columns beyond the caller's grid buffer
+    std::vector<double> own_scratch;
+    std::vector<int32_t> idx_buf;
+    int n_known = 0;                                                  // nodes whose columns exist
+
+    // find_node spawned nodes n_known .. size-1 while datum n was being placed
+    int spawn_refresh(int n)
+    {
+        const int K = (int)t.parent.size(), T = s->ntps, first = n_known, m = K - first;
+        for (int k = first; k < K; k++) {
+            const int pk = t.parent[k];
+            const double frac = s->spawn_frac[k - s->n_nodes];
+            s->tree_parent[k] = pk;
+            for (int tp = 0; tp < T; tp++) {                          // alleles.py:35-37
+                const double child = frac * s->pi[(size_t)pk * T + tp];
+                s->pi[(size_t)k * T + tp] = child;
+                s->pi[(size_t)pk * T + tp] = s->pi[(size_t)pk * T + tp] - child;
+                s->phi[(size_t)k * T + tp] = child;
+            }
+        }
+        if (pwgs_set_tree(s->ctx, K, s->tree_parent, nullptr, s->phi, s->pi) != PWGS_OK) return -8;
+        double *dst;
+        if (K <= s->cap_cols) dst = s->grid + (size_t)first * s->n_data;
+        else {                                                        // one block for the event: its columns stay adjacent
+            own_cols.emplace_back(new double[(size_t)m * s->n_data]);
+            dst = own_cols.back().get();
+        }
+        for (int i = 0; i < m; i++) s->cols[first + i] = dst + (size_t)i * s->n_data;
+        idx_buf.resize(m);
+        for (int i = 0; i < m; i++) idx_buf[i] = first + i;
+        const int rows = s->n_data - n;
+        if (pwgs_llh_range_pitched(s->ctx, n, rows, m, idx_buf.data(), PWGS_SEM_PY | PWGS_LAYOUT_COLS, dst + n, s->n_data) != PWGS_OK) return -8;
+        n_known = K;
+        s->n_refreshes++;
+        return 0;
+    }
+
+    // CNV datum n moved to node k: the rows of its SSMs that are still to be visited change in every node
+    int cnv_refresh(int n, int k)
+    {
+        const int32_t dn = n, dk = k;
+        if (pwgs_move_data(s->ctx, 1, &dn, &dk) != PWGS_OK) return -8;
+        const int j = n - s->n_ssm;
+        const int32_t *lo = s->ssm_idx + s->ssm_ptr[j], *hi = s->ssm_idx + s->ssm_ptr[j + 1];
+        while (lo < hi && *lo <= n) lo++;                             // ascending: skip the rows already visited
+        const int nr = (int)(hi - lo), K = (int)t.parent.size();
+        if (nr == 0) return 0;
+        double *block = s->scratch;
+        if ((int64_t)nr * K > s->scratch_len || !block) {
+            own_scratch.resize((size_t)nr * K);
+            block = own_scratch.data();
+        }
+        if (pwgs_llh_block(s->ctx, nr, lo, 0, nullptr, PWGS_SEM_PY | PWGS_LAYOUT_COLS, block) != PWGS_OK) return -8;
+        for (int c = 0; c < K; c++) {
+            double *col = s->cols[c];
+            const double *src = block + (size_t)c * nr;
+            for (int i = 0; i < nr; i++) col[lo[i]] = src[i];
+        }
+        s->n_refreshes++;
+        return 0;
+    }
+
     int run()
     {
         std::vector<int> cur_path, cand_path;
         int mirrored = s->n_spawned;
+        const bool native = s->on_spawn == nullptr;
+        n_known = (int)t.parent.size();
         for (int n = 0; n < s->n_data; n++) {
             const int cur = s->assignments[n];
             path_of(cur, cur_path);
@@ -126,14 +196,18 @@ struct Sampler {
                 if (err) return err;
                 if (t.parent[cand] < 0) { cand = t.kids[cand][0]; cand_path.assign(1, 0); }       // tssb.py:118-120
                 if (s->n_spawned != mirrored) {
-                    if (s->on_spawn(s->user, n) != 0) return -6;                                  // new columns are now in s->cols
+                    if (native) { if (int rc = spawn_refresh(n)) return rc; }
+                    else if (s->on_spawn(s->user, n) != 0) return -6;                             // new columns are now in s->cols
                     mirrored = s->n_spawned;
                 }
                 if (s->cols[cand][n] > llh_s) {
                     if (cand != cur) {
                         s->assignments[n] = cand;
                         s->n_moved++;
-                        if (n >= s->n_ssm && s->on_cnv_move(s->user, n) != 0) return -7;          // rows of its SSMs still to come
+                        if (n >= s->n_ssm) {                                                      // rows of its SSMs still to come
+                            if (native) { if (int rc = cnv_refresh(n, cand)) return rc; }
+                            else if (s->on_cnv_move(s->user, n) != 0) return -7;
+                        }
                     }
                     break;
                 }
@@ -151,7 +225,13 @@ struct Sampler {
 
 extern "C" int pwgs_resample_assignments(pwgs_sweep *s)
 {
-    if (!s || !s->assignments || !s->cols || !s->uniforms || !s->on_spawn || !s->on_cnv_move) return PWGS_EINVAL;
+    if (!s || !s->assignments || !s->cols || !s->uniforms) return PWGS_EINVAL;
+    if ((s->on_spawn == nullptr) != (s->on_cnv_move == nullptr)) return PWGS_EINVAL;
+    if (!s->on_spawn) {                                                                           // the library refreshes the grid itself
+        if (!s->ctx || !s->tree_parent || !s->phi || !s->pi || s->ntps <= 0 || (s->cap_cols > 0 && !s->grid)) return PWGS_EINVAL;
+        if (s->n_data > s->n_ssm && (!s->ssm_ptr || !s->ssm_idx)) return PWGS_EINVAL;
+        s->n_refreshes = 0;
+    }
     if (s->n_nodes <= 0 || s->n_nodes > s->cap_nodes) return PWGS_EINVAL;
     Sampler S;
     S.s = s;
@@ -163,6 +243,8 @@ extern "C" int pwgs_resample_assignments(pwgs_sweep *s)
     t.depth.assign(K, 0);
     t.kids.assign(K, {});
     t.sticks.assign(K, {});
+    t.edges.assign(K, {});
+    t.rem.assign(K, 1.0);
     for (int k = 0; k < K; k++) {
         for (int c = s->child_ptr[k]; c < s->child_ptr[k + 1]; c++) {
             const int ch = s->child_idx[c];
@@ -170,6 +252,8 @@ extern "C" int pwgs_resample_assignments(pwgs_sweep *s)
             t.index_in_parent[ch] = (int)t.kids[k].size();
             t.kids[k].push_back(ch);
             t.sticks[k].push_back(s->child_stick[c]);
+            t.rem[k] *= 1.0 - s->child_stick[c];
+            t.edges[k].push_back(1.0 - t.rem[k]);
         }
     }
     if (t.parent[0] >= 0) return PWGS_EINVAL;                                                     // node 0 is the root

@@ -154,6 +154,15 @@ class GpuBackend(Backend):
         if os.environ.get("PWGS_MH_BIG"):                   # tuning: -1 automatic, 1 / 0 force / forbid node tables in global memory
             self.engine.set_option("mh_big", int(os.environ["PWGS_MH_BIG"]))
 
+    @property
+    def native_ctx(self):
+        """pwgs_ctx* for library code that talks to the device itself (the native assignment sweep's grid refreshes)."""
+        return self.engine._h
+
+    def tree_grew(self, K):
+        """The library appended nodes to the device's tree (spawns of a native sweep)."""
+        self.engine.K = K
+
     def set_tree_arrays(self, parent, node_of_datum, phi, pi):
         self.engine.set_tree(parent, node_of_datum, phi, pi)
 

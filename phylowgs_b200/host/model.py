@@ -211,7 +211,7 @@ class TSSB(object):
     # the generator and the device context are process-local: keep them out of trees.zip / state pickles
     def __getstate__(self):
         st = dict(self.__dict__)
-        for key in ("backend", "rng", "ustream", "_ssms_of_cnv", "_tree_pickler", "_nod_cache", "_assign_version"):
+        for key in ("backend", "rng", "ustream", "_ssms_of_cnv", "_ssms_csr", "_tree_pickler", "_nod_cache", "_assign_version"):
             st.pop(key, None)
         return st
 

@@ -72,7 +72,7 @@ class _Grid(object):
       * an SSM moved: nothing (no other datum's likelihood looks at it).
     """
 
-    def __init__(self, tssb):
+    def __init__(self, tssb, cap_nodes=0):
         self.tssb = t = tssb
         self.backend = b = t.backend
         from .backend import flatten_tree
@@ -92,7 +92,7 @@ class _Grid(object):
         # the tree as arrays, kept in step with the spawns of the sweep (rows appended; a spawn also changes its parent's pi):
         # re-reading every node object at each of the ~100 refreshes of a sweep cost more than the refreshes themselves
         K = len(self.nodes)
-        cap = max(64, 2 * K)
+        cap = max(64, 2 * K, cap_nodes)
         self._parent = np.zeros(cap, dtype=np.int32)
         self._phi = np.zeros((cap, phi.shape[1]))
         self._pi = np.zeros((cap, phi.shape[1]))
@@ -248,7 +248,10 @@ class _Sweep(C.Structure):
                 ("min_depth", C.c_int32), ("max_depth", C.c_int32), ("cap_spawn", C.c_int32), ("n_spawned", C.c_int32),
                 ("spawn_parent", _ip), ("spawn_stick", _dp), ("spawn_main", _dp), ("spawn_frac", _dp),
                 ("user", C.c_void_p), ("on_spawn", _CB), ("on_cnv_move", _CB), ("refill", _CB0),
-                ("n_moved", C.c_int32), ("n_shrunk", C.c_int32), ("uniforms_used", C.c_int32)]
+                ("n_moved", C.c_int32), ("n_shrunk", C.c_int32), ("uniforms_used", C.c_int32),
+                ("ctx", C.c_void_p), ("ntps", C.c_int32), ("cap_cols", C.c_int32), ("tree_parent", _ip), ("phi", _dp), ("pi", _dp),
+                ("grid", _dp), ("ssm_ptr", _ip), ("ssm_idx", _ip), ("scratch", _dp), ("scratch_len", C.c_int64),
+                ("n_refreshes", C.c_int32)]
 
 
 def resample_assignments_native(tssb):
@@ -259,10 +262,14 @@ def resample_assignments_native(tssb):
     t_start = time.perf_counter()
     t_cb = [0.0, 0, 0, 0.0]                             # seconds inside callbacks, spawn events, CNV moves, seconds mirroring spawns
     lib = _lib.load()
-    grid = _Grid(tssb)
+    cap_spawn = 8192
+    # the library refreshes the grid itself after spawns / CNV moves when the backend is a device context (no callback into
+    # Python per tree edit); other backends (the CPU oracle of the parity tests) are asked through the callbacks
+    ctx = None if os.environ.get("PWGS_SWEEP_CALLBACKS", "0") == "1" else getattr(tssb.backend, "native_ctx", None)
+    grid = _Grid(tssb, cap_nodes=(len(tssb.get_nodes()) + cap_spawn) if ctx else 0)
     t_grid = time.perf_counter()
     N, K0 = tssb.num_data, len(grid.nodes)
-    cap_nodes, cap_spawn = K0 + 8192, 8192
+    cap_nodes = K0 + cap_spawn
     stream = UniformStream(tssb.rng, _uniform_block(tssb))
 
     parent = np.array([-1 if nd.parent() is None else grid.uid[id(nd.parent())] for nd in grid.nodes], dtype=np.int32)
@@ -336,6 +343,28 @@ def resample_assignments_native(tssb):
             return 0
 
     cb_spawn, cb_cnv, cb_refill = _CB(on_spawn), _CB(on_cnv_move), _CB0(refill)
+    if ctx:
+        cb_spawn, cb_cnv = _CB(), _CB()                    # NULL: the library does it
+        if not hasattr(tssb, "_ssms_csr"):                  # CSR over the CNV data: the SSMs linked to each, ascending
+            n_ssm, n_cnv = tssb.backend.n_ssm, N - tssb.backend.n_ssm
+            ptr = np.zeros(n_cnv + 1, dtype=np.int32)
+            chunks = []
+            for j in range(n_cnv):
+                rows = tssb._ssms_of_cnv.get(n_ssm + j)
+                if rows is not None:
+                    chunks.append(rows)
+                    ptr[j + 1] = len(rows)
+            np.cumsum(ptr, out=ptr)
+            tssb._ssms_csr = (ptr, np.concatenate(chunks).astype(np.int32) if chunks else np.zeros(1, dtype=np.int32))
+        ssm_ptr, ssm_idx = tssb._ssms_csr
+        sw.ctx, sw.ntps, sw.cap_cols = ctx, grid._phi.shape[1], grid._full.shape[0]
+        assert grid._parent.shape[0] >= cap_nodes and grid._full.flags.c_contiguous
+        sw.tree_parent, sw.phi, sw.pi = grid._parent.ctypes.data_as(_ip), grid._phi.ctypes.data_as(_dp), grid._pi.ctypes.data_as(_dp)
+        sw.grid = grid._full.ctypes.data_as(_dp)
+        sw.ssm_ptr, sw.ssm_idx = ssm_ptr.ctypes.data_as(_ip), ssm_idx.ctypes.data_as(_ip)
+        scratch = getattr(tssb.backend, "_scratch", None)
+        if scratch is not None and len(scratch):
+            sw.scratch, sw.scratch_len = scratch.ctypes.data_as(_dp), len(scratch)
     sw.n_data, sw.n_ssm, sw.n_nodes, sw.cap_nodes = N, tssb.backend.n_ssm, K0, cap_nodes
     sw.parent, sw.main = parent.ctypes.data_as(_ip), main.ctypes.data_as(_dp)
     sw.child_ptr, sw.child_idx, sw.child_stick = child_ptr.ctypes.data_as(_ip), child_idx.ctypes.data_as(_ip), child_stick.ctypes.data_as(_dp)
@@ -353,8 +382,14 @@ def resample_assignments_native(tssb):
     if failure:
         raise failure[0]
     if rc != 0:
-        raise RuntimeError("pwgs_resample_assignments failed with code %d" % rc)
+        raise RuntimeError("pwgs_resample_assignments failed with code %d%s" % (rc, (": " + lib.pwgs_last_error().decode()) if rc == -8 else ""))
+    t_m = time.perf_counter()
     mirror_spawns()
+    if ctx:
+        t_cb[3] += time.perf_counter() - t_m
+        grid.nod[:] = assign
+        grid.calls += sw.n_refreshes
+        tssb.backend.tree_grew(len(grid.nodes))
     for _ in range(sw.n_shrunk):
         sys.stderr.write("Slice sampler shrank down.  Keep current state.\n")
     # mirror the moves back into the Python objects: set operations per node, two stores per moved datum
