@@ -14,6 +14,8 @@
 """
 import ctypes as C
 import math
+from collections import deque
+from itertools import repeat
 import os
 import sys
 
@@ -400,11 +402,11 @@ def resample_assignments_native(tssb):
             ks, starts = np.unique(key[order], return_index=True)
             for k, chunk in zip(ks.tolist(), np.split(changed[order], starts[1:])):
                 getattr(grid.nodes[k].data, op)(chunk.tolist())
-        nodes, assignments, data = grid.nodes, tssb.assignments, tssb.data
-        for n, k in zip(changed.tolist(), assign[changed].tolist()):
-            nd = nodes[k]
-            assignments[n] = nd
-            data[n].node = nd
+        # two stores per moved datum, as loops inside the interpreter's C code (deque(map(...), maxlen=0) runs the map dry)
+        moved = changed.tolist()
+        targets = list(map(grid.nodes.__getitem__, assign[changed].tolist()))
+        deque(map(tssb.assignments.__setitem__, moved, targets), maxlen=0)
+        deque(map(setattr, map(tssb.data.__getitem__, moved), repeat("node"), targets), maxlen=0)
     # the assignments as an array, for the next flatten_tree (the set operations above went around Node.add_datum)
     tssb.__dict__["_nod_cache"] = (getattr(tssb, "_assign_version", 0), list(grid.nodes), assign.copy())
     tssb.last_grid_refreshes = grid.calls
