@@ -28,6 +28,9 @@ The patches.  Each is syntax-level; none changes what a line computes under Pyth
                                                               ran on did not, so data.py:97 `max(0, ...)` is the builtin)
   P8  `dtype='string'` -> dtype=str (params.py:62); file modes 'rU' -> 'r' (util2.py:55,74); pickle files opened in binary
       mode (util2.py:199,206,209); `freq.keys()` wrapped in list() (evolve.py:268)
+  P9  pwgsresults only (`load_results`): `assert new_idx < sidx` with new_idx None (result_munger.py:290; Python 2 orders None
+      before every int, Python 3 raises) -> `assert new_idx is None or new_idx < sidx`; `np.linalg.linalg.LinAlgError`
+      (json_writer.py:27,33; the private module is gone from numpy 2) -> `np.linalg.LinAlgError`
 Python-2 builtins restored in each module's globals before it runs: map / filter / range / zip returning lists, cmp, reduce,
 xrange.  `scipy.misc` (comb, logsumexp — removed from SciPy) is provided as a two-function stand-in module, and printo.py
 (tree drawing through ete2; evolve.py imports it and never calls it) as an empty one.
@@ -208,3 +211,81 @@ class Reference(object):
 
 def load(**kw):
     return Reference(**kw)
+
+
+RESULT_MODULES = ["index_calculator", "result_generator", "result_munger", "json_writer"]
+
+
+def load_results(ref):
+    """The reference's pwgsresults package (write_results.py:3-5), exec'd like the rest (P1-P9), on top of a loaded `Reference`
+    (result_generator.py imports the reference's util2).  -> namespace with ResultGenerator, ResultMunger, IndexCalculator,
+    calc_tree_densities.  JsonWriter's file writing is Python-2 only (json.dump into a binary gzip stream); callers compare the
+    structures it would dump."""
+    assert "util2" in ref.names
+    pkg = types.ModuleType("pwgsresults")
+    pkg.__path__ = [os.path.join(REF, "pwgsresults")]
+    saved = {n: sys.modules.get(n) for n in ["pwgsresults"] + ["pwgsresults." + m for m in RESULT_MODULES]}
+    sys.modules["pwgsresults"] = pkg
+    out = types.SimpleNamespace()
+    try:
+        for name in RESULT_MODULES:
+            path = os.path.join(REF, "pwgsresults", name + ".py")
+            with open(path) as f:
+                src = patch_source(name + ".py", f.read())
+            src = src.replace("assert new_idx < sidx", "assert new_idx is None or new_idx < sidx")      # P9
+            src = src.replace("np.linalg.linalg.LinAlgError", "np.linalg.LinAlgError")
+            mod = types.ModuleType("pwgsresults." + name)
+            mod.__file__ = path
+            sys.modules["pwgsresults." + name] = mod
+            setattr(pkg, name, mod)
+            exec(compile(src, path, "exec"), mod.__dict__)
+        out.ResultGenerator = sys.modules["pwgsresults.result_generator"].ResultGenerator
+        out.ResultMunger = sys.modules["pwgsresults.result_munger"].ResultMunger
+        out.IndexCalculator = sys.modules["pwgsresults.index_calculator"].IndexCalculator
+        out.calc_tree_densities = sys.modules["pwgsresults.json_writer"].calc_tree_densities
+    finally:
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
+    return out
+
+
+def reference_results(tree_file, include_ssm_names=False, min_ssms=0.01, keep_superclones=False, include_multiprimary=False,
+                      max_multiprimary=0.8):
+    """What the reference's write_results.py (lines 44-55) would put into its three output files for `tree_file`, as plain JSON
+    values: {"summaries": tree_summary_output, "mutlist": mutlist_output, "mutass": {tree index: member of mutass_output}}
+    (dataset_name left out).  Every number is computed by the reference's own classes."""
+    import contextlib
+    import io
+    import json
+    ref = load()
+    try:
+        R = load_results(ref)
+        with contextlib.redirect_stdout(io.StringIO()):
+            summaries, mutlist, mutass, params = R.ResultGenerator().generate(tree_file, include_ssm_names)
+            munger = R.ResultMunger(summaries, mutlist, mutass)
+            summaries, mutass = munger.remove_small_nodes(min_ssms)
+            if not keep_superclones:
+                munger.remove_superclones()
+            if not include_multiprimary:
+                munger.remove_multiprimary_trees(max_multiprimary)
+        for summary in summaries.values():                                   # json_writer.py:55-59
+            calc = R.IndexCalculator(summary)
+            summary["linearity_index"] = calc.calc_linearity_index()
+            summary["branching_index"] = calc.calc_branching_index()
+            summary["clustering_index"] = calc.calc_clustering_index()
+        out = {"summaries": {"params": params, "trees": summaries, "tree_densities": R.calc_tree_densities(summaries)},
+               "mutlist": mutlist, "mutass": {idx: {"mut_assignments": m} for idx, m in mutass.items()}}
+
+        def plain(o):
+            import numpy as np
+            if isinstance(o, np.ndarray):
+                return o.tolist()
+            if isinstance(o, np.generic):
+                return o.item()
+            raise TypeError(repr(o))
+        return json.loads(json.dumps(out, default=plain))
+    finally:
+        ref.release()
