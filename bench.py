@@ -562,7 +562,9 @@ def main():
                     if k >= 3:
                         ks.append(max(r_["kernel_ms"] for r_ in rr))
                 chains_per_gpu.append({"chains": C_, "sms_per_chain": eng.get_option("n_sms") // C_, "value": C_ * MH_ITR / (statistics.mean(ks) * 1e-3),
-                                       "unit": UNIT, "kernel_ms_per_launch": statistics.mean(ks)})
+                                       "unit": UNIT, "kernel_ms_per_launch": statistics.mean(ks),
+                                       # the same instruction model as `roofline`, all chains of the launch together
+                                       "roofline_frac": (fp_it * C_ * MH_ITR / (statistics.mean(ks) * 1e-3) / fp64_peak) if fp_it else None})
         finally:
             for e2 in extra:
                 e2.close()
@@ -653,6 +655,11 @@ def main():
                 "algorithmic_fp64_instr_per_iteration": fp_it, "kernel_ms_per_launch": kms,
                 "frac_on_round1_instruction_model": algorithmic_work_r1(s, stats) * its_kernel / fp64_peak,
                 "round1_model_fp64_instr_per_iteration": algorithmic_work_r1(s, stats),
+                # SURVEY.md 8d's own per-unit figure (the reference's dense 4-state formulation with libm: 66 per plain term,
+                # 8K + 400 per CNV-affected SSM): > 1 means the kernel gets the iteration done with less arithmetic than that
+                # formulation needs at the pipe's peak -- an algorithmic gain (sparse merged states, table-driven log), not utilisation
+                "survey_8d_model_fp64_instr_per_iteration": float(T * (66 * (D - M) + (8 * K + 400) * M)),
+                "frac_on_survey_8d_model": float(T * (66 * (D - M) + (8 * K + 400) * M)) * its_kernel / fp64_peak,
                 "note": "frac = FP64-pipe instructions this cubin executes per completed iteration (profiles/r02_mh_kernel_sass_histogram.txt: "
                         "9 per logarithm) x it/s / measured DFMA peak = the pipe utilisation ncu reports; the round-1 model (16 per "
                         "logarithm) is the same work counted the way BENCH_r01 counted it",

@@ -59,7 +59,7 @@ def assignment_array(tssb, nodes):
 def flatten_tree(tssb):
     """Preorder node list (get_mixture order = the ids evolve.py:175-177 assigns) -> (nodes, parent, node_of_datum, phi, pi).
     The tree is flattened three times per MCMC iteration; node_of_datum comes from `assignment_array`'s cache."""
-    _, nodes = tssb.get_mixture()
+    nodes = tssb.get_nodes()                               # preorder, as get_mixture lists them (without computing the weights)
     pos = {id(nd): k for k, nd in enumerate(nodes)}
     parent = np.array([-1 if nd.parent() is None else pos[id(nd.parent())] for nd in nodes], dtype=np.int32)
     nod = assignment_array(tssb, nodes)

@@ -282,9 +282,16 @@ class TSSB(object):
         def walk(entry, mass):
             weights.append(mass * entry["main"])
             nodes.append(entry["node"])
-            w = np.diff(np.hstack([0.0, sticks_to_edges(entry["sticks"])]))
-            for i, child in enumerate(entry["children"]):
-                walk(child, mass * (1.0 - entry["main"]) * w[i])
+            if entry["children"]:
+                # widths of the children's intervals, diff of 1 - cumprod(1 - sticks) (util.py:11-12), in plain floats: the same
+                # operations in the same order as the array expression (checked in tests/test_stick_orders.py), without
+                # numpy's per-call overhead on the mostly tiny stick arrays -- the tree is walked several times per MCMC iteration
+                rest, rem, left = mass * (1.0 - entry["main"]), 1.0, 0.0
+                for child, s in zip(entry["children"], entry["sticks"][:, 0].tolist()):
+                    rem *= 1.0 - s
+                    edge = 1.0 - rem
+                    walk(child, rest * (edge - left))
+                    left = edge
         walk(self.root, 1.0)
         return weights, nodes
 

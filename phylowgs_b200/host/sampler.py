@@ -274,22 +274,27 @@ def resample_assignments_native(tssb):
     cap_nodes = K0 + cap_spawn
     stream = UniformStream(tssb.rng, _uniform_block(tssb))
 
-    parent = np.array([-1 if nd.parent() is None else grid.uid[id(nd.parent())] for nd in grid.nodes], dtype=np.int32)
+    parent = grid._parent[:K0].copy()
     main = np.array([e["main"] for e in grid.entries], dtype=np.float64)
     child_ptr = np.zeros(K0 + 1, dtype=np.int32)
     child_idx, child_stick = [], []
+    uid = grid.uid
     for k, e in enumerate(grid.entries):
-        for i, c in enumerate(e["children"]):
-            child_idx.append(grid.uid[id(c["node"])])
-            child_stick.append(float(np.ravel(e["sticks"][i])[0]))
+        if e["children"]:
+            child_idx += [uid[id(c["node"])] for c in e["children"]]
+            child_stick += e["sticks"][:len(e["children"]), 0].tolist()
         child_ptr[k + 1] = len(child_idx)
     child_idx = np.array(child_idx if child_idx else [0], dtype=np.int32)
     child_stick = np.array(child_stick if child_stick else [0.0], dtype=np.float64)
     assign = grid.nod.copy()
     before = assign.copy()
-    cols = (_dp * cap_nodes)()
-    for k, col in enumerate(grid.cols):
-        cols[k] = col.ctypes.data_as(_dp)
+    # cols[k] = address of node k's column: rows of the sweep's buffer (one vector expression), library-owned memory beyond
+    col_addr = np.zeros(cap_nodes, dtype=np.uint64)
+    full_rows = grid._full.shape[0]
+    col_addr[:full_rows] = grid._full.ctypes.data + np.arange(full_rows, dtype=np.uint64) * np.uint64(grid._full.strides[0])
+    assert K0 <= full_rows
+    col_addr[K0:] = 0
+    cols = C.cast(col_addr.ctypes.data, C.POINTER(_dp))
     sp_parent = np.zeros(cap_spawn, dtype=np.int32)
     sp_stick, sp_main, sp_frac = np.zeros(cap_spawn), np.zeros(cap_spawn), np.zeros(cap_spawn)
     failure = []
@@ -315,7 +320,7 @@ def resample_assignments_native(tssb):
             t_cb[3] += time.perf_counter() - t0
             grid.fetch_new_columns(int(n), first)
             for k in range(first, len(grid.nodes)):
-                cols[k] = grid.cols[k].ctypes.data_as(_dp)
+                col_addr[k] = grid.cols[k].ctypes.data
             return 0
         except BaseException as e:          # noqa: B902 - must not propagate through the C frame
             failure.append(e)

@@ -91,3 +91,21 @@ def test_fast_path_equals_the_array_formulation():
         assert shape(a) == shape(b), seed
         assert a.rng.rand() == b.rng.rand(), seed                  # the generators consumed the same draws
         assert getattr(a, "n_spawned", 0) == getattr(b, "n_spawned", 0)
+
+
+def test_get_mixture_in_plain_floats_equals_the_array_expression():
+    """get_mixture's scalar walk against tssb.py:389-402 written with arrays (diff of 1 - cumprod(1 - sticks)): same bits."""
+    t = random_tree(8, 60, 30, 0)
+    want_w, want_n = [], []
+
+    def walk(entry, mass):
+        want_w.append(mass * entry["main"])
+        want_n.append(entry["node"])
+        w = np.diff(np.hstack([0.0, sticks_to_edges(entry["sticks"])]))
+        for i, child in enumerate(entry["children"]):
+            walk(child, mass * (1.0 - entry["main"]) * w[i])
+    walk(t.root, 1.0)
+    got_w, got_n = t.get_mixture()
+    assert all(a is b for a, b in zip(got_n, want_n)) and len(got_n) == 61
+    assert [float(x).hex() for x in got_w] == [float(x).hex() for x in want_w]
+    assert got_n == t.get_nodes()
