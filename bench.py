@@ -237,7 +237,7 @@ def ncu_traffic_bytes():
     return best
 
 
-def tree_sample_rate(s, device, iterations=6, cpu_mh=None, cpu_seconds=10.0):
+def tree_sample_rate(s, device, iterations=12, cpu_mh=None, cpu_seconds=10.0):
     """Secondary figure of BASELINE's metric: full MCMC tree samples/s of one chain through the host glue (evolve.py:148-230:
     assignment sweep + MH + sticks/hypers + LLH trace + pickling) on the same workload, the first iteration discarded.  The
     reference's Python-2 side cannot run here, so there is no CPU number beside it (its sweep is O(N^2))."""
@@ -270,6 +270,7 @@ def tree_sample_rate(s, device, iterations=6, cpu_mh=None, cpu_seconds=10.0):
     for d in codes:
         d.tssb = tssb
     mh_std, times, parts = MH_STD, [], []
+    E.freeze_long_lived()                              # as evolve.do_mcmc does
     for it in range(iterations):
         t = [time.perf_counter()]
         tssb.resample_assignments(); t.append(time.perf_counter())
@@ -291,6 +292,7 @@ def tree_sample_rate(s, device, iterations=6, cpu_mh=None, cpu_seconds=10.0):
     p = np.median(np.array(parts[1:]), axis=0)
     out = {"value": 1.0 / med, "unit": "tree samples/s", "iterations": iterations - 1, "mh_iterations_per_sample": MH_ITR,
            "seconds": {"assignment_sweep": float(p[0]), "metropolis": float(p[1]), "sticks_hypers_llh": float(p[2]), "pickle": float(p[3])},
+           "seconds_per_iteration": [round(x, 5) for x in times],
            "note": "burn-in iterations from the one-node start (many spawned nodes)"}
     if cpu_mh is not None:
         # ---- the CPU beside it ("Python half"): the reference's sweep and LLH trace, restated in plain
