@@ -408,6 +408,9 @@ static_assert(PWGS_MAX_BATCH / 32 <= MH_CWARPS, "the publish / read-totals steps
 #define MH_WIDE_AFTER 8                  // this many all-reject batches in a row: an accept wastes the rest of its batch, so the wide
                                          // batch (half as many chain barriers per iteration) only pays at very low acceptance
 #define MH_DIST_MIN_CTAS 8               // chains with fewer CTAs draw every proposal locally in every CTA
+#ifndef MH_EPOCH_LOCAL
+#define MH_EPOCH_LOCAL 1                 // epochs whose first two batches fit one round of local draws start without a chain barrier
+#endif
 
 struct MhParams {
     int Dp, M, T, K;
@@ -475,13 +478,14 @@ enum MhCtl { CTL_GEN = 0, CTL_DONE = 1, CTL_PROD_DONE = 2, CTL_ABORT = 3, CTL_JO
 //   pi1   [maxb][KT]                       proposal b, node/sample i at b*KT + i
 //   phi1  [ceil(maxb/4)][KT][4]            proposal b, node/sample i at mh_phi_at(b, i, KT): the four proposals a likelihood thread
 //                                          evaluates together are adjacent, so it reads them with two 16-byte loads
-//   hastings [maxb][T], log r [maxb]
+//   hastings [maxb][T][3]: {Hastings correction, sum_k lgamma(mh_std*pi1_k), lgamma(sum_k mh_std*pi1_k)} -- the two lgamma terms
+//                          are what the chain state needs if this proposal is accepted (no lgamma pass on the accept path);  log r [maxb]
 // Region offsets are even so that the phi region is 16-byte aligned.
 __host__ __device__ inline size_t mh_even(size_t x) { return (x + 1) & ~(size_t)1; }
 __host__ __device__ inline size_t mh_phi_doubles(int KT, int nb) { return (size_t)((nb + 3) & ~3) * KT; }
 __host__ __device__ inline size_t mh_o_phi(int KT, int maxb) { return mh_even((size_t)maxb * KT); }
 __host__ __device__ inline size_t mh_o_hast(int KT, int maxb) { return mh_o_phi(KT, maxb) + mh_phi_doubles(KT, maxb); }
-__host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return mh_even(mh_o_hast(K * T, maxb) + (size_t)maxb * T + maxb); }
+__host__ __device__ inline size_t mh_bufstride(int K, int T, int maxb) { return mh_even(mh_o_hast(K * T, maxb) + 3 * (size_t)maxb * T + maxb); }
 __host__ __device__ __forceinline__ int mh_phi_at(int b, int i, int KT) { return (b >> 2) * 4 * KT + i * 4 + (b & 3); }
 // the part that grows with the tree: two state copies, two proposal buffers, the draw scratch of every warp.  Normally in shared
 // memory; mh_kernel<false, true> keeps it in global memory (p.gscratch), one region per CTA
@@ -569,7 +573,9 @@ __device__ __noinline__ void mh_propose(const MhParams &p, const MhSmem &S, int 
     if (lane == 0) {
         double lp1 = t1 + lgs - slg;
         double lp2 = t2 + S.lgsum(e)[tp] - S.slg(e)[tp];
-        *hast_out = lp1 - lp2;
+        hast_out[0] = lp1 - lp2;
+        hast_out[1] = slg;                                                       // the state's slg / lgsum once this proposal is
+        hast_out[2] = lgs;                                                       // accepted (same bits as mh_refresh_state computes)
         if (tp == 0) {
             double u0, u1;
             stream_draw(p.seed, p.stream, it, 0, 0, PWGS_PURPOSE_ACCEPT, 0, u0, u1);
@@ -585,8 +591,25 @@ __device__ __forceinline__ void mh_draw_local(const MhParams &p, const MhSmem &S
 #pragma unroll 1
     for (int task = warp; task < nb * T; task += MH_CWARPS) {
         const int b = task / T, tp = task - b * T;
-        mh_propose(p, S, e, S.prop_pi(buf) + b * KT + tp, S.prop_phi(buf) + mh_phi_at(b, tp, KT), T, 4 * T, S.hast(buf) + b * T + tp,
+        mh_propose(p, S, e, S.prop_pi(buf) + b * KT + tp, S.prop_phi(buf) + mh_phi_at(b, tp, KT), T, 4 * T, S.hast(buf) + 3 * (b * T + tp),
                    S.logr(buf) + b, tp, (uint32_t)(it_first + b), lane);
+    }
+}
+
+// Start of an epoch whose first two batches are small enough for ONE round of draws by this CTA's own warps ((n0 + n1) * T <=
+// MH_CWARPS): batch n0 goes into buffer `buf`, batch n1 into the other one, where the main loop expects the batch after.  Every
+// CTA draws the same proposals (they are functions of the state and the iteration alone), so no chain barrier and no copy out of
+// the epoch slots is needed: at acceptance rates of 10 % and more, where an accept comes every few iterations, this is most
+// epochs and saves ~4k of the ~26k cycles an accept costs.  Out of line: cold code.
+__device__ __noinline__ void mh_epoch_local(const MhParams &p, const MhSmem &S, int e, int buf, int n0, int it0, int n1, int warp, int lane)
+{
+    const int T = p.T, KT = p.K * T;
+#pragma unroll 1
+    for (int task = warp; task < (n0 + n1) * T; task += MH_CWARPS) {
+        const int bsel = task / T, tp = task - bsel * T;
+        const int bb = bsel < n0 ? buf : buf ^ 1, b = bsel < n0 ? bsel : bsel - n0;
+        mh_propose(p, S, e, S.prop_pi(bb) + b * KT + tp, S.prop_phi(bb) + mh_phi_at(b, tp, KT), T, 4 * T, S.hast(bb) + 3 * (b * T + tp),
+                   S.logr(bb) + b, tp, (uint32_t)(it0 + bsel), lane);
     }
 }
 
@@ -607,6 +630,20 @@ __device__ __noinline__ void mh_refresh_state(const MhParams &p, const MhSmem &S
         for (int k = lane; k < K; k += 32) { sa += p.mh_std * S.pi(e)[k * T + tp]; sl += S.lg(e)[k * T + tp]; }
         sa = warp_sum(sa); sl = warp_sum(sl);
         if (lane == 0) { S.lgsum(e)[tp] = pwgs_lgamma(sa); S.slg(e)[tp] = sl; }
+    }
+}
+
+// State copy e becomes proposal `sel` of buffer `buf` (its pi / phi are already copied): log(pi), and the two lgamma terms that
+// came with the proposal (mh_propose) -- bit for bit what mh_refresh_state would compute, without its lgamma pass and the second
+// one for the sums (~5k cycles of the ~26k an accept costs).  Out of line: cold code, kept out of the likelihood loops' registers.
+__device__ __noinline__ void mh_adopt_state(const MhSmem &S, int e, int buf, int sel, int tid)
+{
+    const int T = S.T, KT = S.KT;
+#pragma unroll 1
+    for (int i = tid; i < KT; i += MH_CONSUMERS) S.lp(e)[i] = log(S.pi(e)[i]);
+    if (tid < T) {
+        S.slg(e)[tid] = S.hast(buf)[3 * (sel * T + tid) + 1];
+        S.lgsum(e)[tid] = S.hast(buf)[3 * (sel * T + tid) + 2];
     }
 }
 
@@ -897,8 +934,8 @@ __device__ __forceinline__ void mh_draw_to_slot(const MhParams &p, const MhSmem 
 {
     const int T = p.T, K = p.K, KT = K * T;
     double *x = S.pscratch + (size_t)scratch * 2 * K;
-    double hast = 0.0, logr = 0.0;
-    mh_propose(p, S, e, x, x + K, 1, 1, &hast, &logr, tp, it, lane);
+    double hast[3] = {0.0, 0.0, 0.0}, logr = 0.0;
+    mh_propose(p, S, e, x, x + K, 1, 1, hast, &logr, tp, it, lane);
     __syncwarp();
 #pragma unroll 1
     for (int k = lane; k < K; k += 32) {
@@ -906,7 +943,9 @@ __device__ __forceinline__ void mh_draw_to_slot(const MhParams &p, const MhSmem 
         slot[(size_t)S.o_phi + mh_phi_at(b, k * T + tp, KT)] = x[K + k];
     }
     if (lane == 0) {
-        slot[(size_t)S.o_hast + b * T + tp] = hast;
+        slot[(size_t)S.o_hast + 3 * (b * T + tp)] = hast[0];
+        slot[(size_t)S.o_hast + 3 * (b * T + tp) + 1] = hast[1];
+        slot[(size_t)S.o_hast + 3 * (b * T + tp) + 2] = hast[2];
         if (tp == 0) slot[(size_t)S.o_logr + b] = logr;
     }
     __syncwarp();
@@ -983,7 +1022,7 @@ __device__ __noinline__ bool mh_epoch_start(const MhParams &p, const MhSmem &S, 
     double *dst = S.prop_pi(buf);
     for (int i = tid; i < n0 * KT; i += MH_CONSUMERS) dst[i] = __ldcg(es0 + i);
     for (int i = tid; i < (int)mh_phi_doubles(KT, n0); i += MH_CONSUMERS) dst[S.o_phi + i] = __ldcg(es0 + S.o_phi + i);
-    for (int i = tid; i < n0 * T; i += MH_CONSUMERS) dst[S.o_hast + i] = __ldcg(es0 + S.o_hast + i);
+    for (int i = tid; i < 3 * n0 * T; i += MH_CONSUMERS) dst[S.o_hast + i] = __ldcg(es0 + S.o_hast + i);
     for (int i = tid; i < n0; i += MH_CONSUMERS) dst[S.o_logr + i] = __ldcg(es0 + S.o_logr + i);
     return false;
 }
@@ -1021,7 +1060,7 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
         double *t = BIG ? p.gscratch + (size_t)rank * p.gstride : q;
         S.KT = KT; S.T = T; S.statestride = 4 * KT + 2 * T;
         S.state0 = t; t += 2 * S.statestride;
-        S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = (int)mh_o_phi(KT, MAXB); S.o_hast = (int)mh_o_hast(KT, MAXB); S.o_logr = S.o_hast + MAXB * T;
+        S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = (int)mh_o_phi(KT, MAXB); S.o_hast = (int)mh_o_hast(KT, MAXB); S.o_logr = S.o_hast + 3 * MAXB * T;
         S.buf0 = t; t += 2 * S.bufstride;
         S.pscratch = t; t += 2 * K * (MH_CWARPS + 1);
         if (!BIG) q = t;
@@ -1117,7 +1156,8 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
     int accepted = 0;
     int g = 0;                                         // global batch number (proposal ring slots, partial-sum parity)
     unsigned long long bar_no = 0;                     // chain barriers passed so far (one per batch + one per accept)
-    bool es_ready = false;                             // the second batch of the current epoch waits in epoch slot 1
+    int es_ready = 0;                                  // the second batch of the current epoch waits in epoch slot 1 (1), or is
+                                                       // already in the other proposal buffer (2: mh_epoch_local)
     double cur_llh = 0.0;
 
 #pragma unroll 1
@@ -1190,7 +1230,8 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
         MH_PROF(1);
 
         // ---------------- while the barrier is in flight: draw the next batch locally when the ring cannot provide it
-        const bool next_local = !dist || j < 0 || (j == 0 && !es_ready);
+        const bool have_next = j == 0 && es_ready == 2;
+        const bool next_local = !dist || j < 0 || (j == 0 && es_ready == 0);
         if (next_local) mh_draw_local(p, S, e, cur ^ 1, n1_nb, n1_it, warp, lane);
         MH_PROF(2);
         if (tid == 0) {
@@ -1212,14 +1253,16 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
         // ---------------- every CTA reads the same integer totals -> bit-identical decisions everywhere;
         // the loads of the next batch's ring slot (complete: every CTA posted its share before arriving) go out first so that
         // all L2 round trips of this step overlap
-        const bool fetch = !next_local && n1_nb > 0;
+        const bool fetch = !next_local && !have_next && n1_nb > 0;
         const double *slot = p.ring + (size_t)(j == 0 ? MH_RING + 1 : (g + 1) % MH_RING) * (size_t)S.bufstride;   // epoch slot 1 / ring
-        double f_pi = 0.0, f_phi = 0.0, f_h = 0.0, f_r = 0.0;
+        double f_pi = 0.0, f_phi = 0.0, f_h = 0.0, f_h2 = 0.0, f_h3 = 0.0, f_r = 0.0;
         const int n1_phi = (int)mh_phi_doubles(KT, n1_nb);
         if (fetch) {
             if (tid < n1_nb * KT) f_pi = __ldcg(slot + tid);
             if (tid < n1_phi) f_phi = __ldcg(slot + S.o_phi + tid);
-            if (tid < n1_nb * T) f_h = __ldcg(slot + S.o_hast + tid);
+            if (tid < 3 * n1_nb * T) f_h = __ldcg(slot + S.o_hast + tid);                  // the three-word Hastings records: all of a
+            if (tid + MH_CONSUMERS < 3 * n1_nb * T) f_h2 = __ldcg(slot + S.o_hast + tid + MH_CONSUMERS);           // full batch at T = 1 in this
+            if (tid + 2 * MH_CONSUMERS < 3 * n1_nb * T) f_h3 = __ldcg(slot + S.o_hast + tid + 2 * MH_CONSUMERS);   // one round of loads
             if (tid < n1_nb) f_r = __ldcg(slot + S.o_logr + tid);
         }
         if (warp < PWGS_MAX_BATCH / 32) {
@@ -1235,7 +1278,7 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
                 S.llh[tid] = val;
                 if (j >= 0 && tid < b_nb) {
                     double a = val - cur_llh;
-                    for (int tp = 0; tp < T; tp++) a += S.hast(cur)[tid * T + tp];
+                    for (int tp = 0; tp < T; tp++) a += S.hast(cur)[3 * (tid * T + tp)];
                     ok = S.logr(cur)[tid] < a;
                 }
             }
@@ -1246,11 +1289,13 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
             double *dst = S.prop_pi(cur ^ 1);
             if (tid < n1_nb * KT) dst[tid] = f_pi;
             if (tid < n1_phi) dst[S.o_phi + tid] = f_phi;
-            if (tid < n1_nb * T) dst[S.o_hast + tid] = f_h;
+            if (tid < 3 * n1_nb * T) dst[S.o_hast + tid] = f_h;
+            if (tid + MH_CONSUMERS < 3 * n1_nb * T) dst[S.o_hast + tid + MH_CONSUMERS] = f_h2;
+            if (tid + 2 * MH_CONSUMERS < 3 * n1_nb * T) dst[S.o_hast + tid + 2 * MH_CONSUMERS] = f_h3;
             if (tid < n1_nb) dst[S.o_logr + tid] = f_r;
             for (int i = tid + MH_CONSUMERS; i < n1_nb * KT; i += MH_CONSUMERS) dst[i] = __ldcg(slot + i);
             for (int i = tid + MH_CONSUMERS; i < n1_phi; i += MH_CONSUMERS) dst[S.o_phi + i] = __ldcg(slot + S.o_phi + i);
-            for (int i = tid + MH_CONSUMERS; i < n1_nb * T; i += MH_CONSUMERS) dst[S.o_hast + i] = __ldcg(slot + S.o_hast + i);
+            for (int i = tid + 3 * MH_CONSUMERS; i < 3 * n1_nb * T; i += MH_CONSUMERS) dst[S.o_hast + i] = __ldcg(slot + S.o_hast + i);
         }
         consumer_sync();
         MH_PROF(4);
@@ -1285,17 +1330,21 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
         // after an accept at position sel, expect the next one about as far away: batch = pow2 >= sel+1
         b_nb = pow2_floor(min(min(batch_cap(0, MAXB), max(1, 2 * pow2_floor(sel + 1))), p.iters - b_it));
         j = 0;
+        mh_adopt_state(S, e, cur, sel, tid);
         consumer_sync();
-        mh_refresh_state(p, S, e, tid, warp, lane);
-        consumer_sync();
-        es_ready = false;
+        es_ready = 0;
         if (!dist) {
             mh_draw_local(p, S, e, cur ^ 1, b_nb, b_it, warp, lane);
         } else {
             const int n1b = next_batch(b_nb, p.iters - (b_it + b_nb), batch_cap(1, MAXB));
-            if (mh_epoch_start(p, S, e, cur ^ 1, b_nb, b_it, n1b, rank, cpc, bar_no, tid, warp, lane)) break;
-            bar_no++;
-            es_ready = n1b > 0;
+            if (MH_EPOCH_LOCAL && (b_nb + n1b) * T <= MH_CWARPS) {
+                mh_epoch_local(p, S, e, cur ^ 1, b_nb, b_it, n1b, warp, lane);
+                es_ready = n1b > 0 ? 2 : 0;
+            } else {
+                if (mh_epoch_start(p, S, e, cur ^ 1, b_nb, b_it, n1b, rank, cpc, bar_no, tid, warp, lane)) break;
+                bar_no++;
+                es_ready = n1b > 0 ? 1 : 0;
+            }
         }
         cur ^= 1;
         consumer_sync();

@@ -74,3 +74,34 @@ def test_argument_validation_happens_before_any_device_work(lib):
     assert rc == -1 and b"a <= d" in lib.pwgs_last_error()
     rc = lib.pwgs_create(0, 0, 0, 1, None, None, None, None, None, None, None, None, C.byref(h))
     assert rc == -1
+
+
+def test_pickle_join_gathers_and_validates(lib):
+    """pwgs_pickle_join (host code): fragment | reference | tail per item, fragments alone for negative references; capacity and
+    index errors are reported, nothing is written past `cap`."""
+    frags = [b"alpha", b"", b"bc", b"delta!"]
+    blob = b"".join(frags)
+    off = np.zeros(5, dtype=np.int64)
+    np.cumsum([len(f) for f in frags], out=off[1:])
+    refs = np.zeros((2, 8), dtype=np.uint8)
+    for k, r in enumerate([b"h\x07", b"j\x01\x02\x03\x04"]):
+        refs[k, 0] = len(r)
+        refs[k, 1:1 + len(r)] = np.frombuffer(r, dtype=np.uint8)
+    ref_of = np.array([1, 0, -1, 0], dtype=np.int32)
+    tail = b"TT"
+    want = b"alpha" + b"j\x01\x02\x03\x04" + tail + b"" + b"h\x07" + tail + b"bc" + b"delta!" + b"h\x07" + tail
+
+    def join(n, ref_of, cap):
+        out = bytearray(max(cap, 1) + 8)
+        w = lib.pwgs_pickle_join(n, blob, off.ctypes.data, ref_of.ctypes.data_as(C.POINTER(C.c_int32)), 2, refs.ctypes.data, tail, len(tail),
+                                 (C.c_char * len(out)).from_buffer(out), cap)
+        return w, bytes(out)
+
+    w, out = join(4, ref_of, 64)
+    assert w == len(want) and out[:w] == want and out[w:] == bytes(len(out) - w)
+    w, out = join(4, ref_of, len(want))
+    assert w == len(want)
+    w, out = join(4, ref_of, len(want) - 1)
+    assert w == -4 and out[len(want) - 1:] == bytes(len(out) - len(want) + 1)    # PWGS_ELIMIT, the bytes beyond cap untouched
+    assert join(4, np.array([2, 0, 0, 0], dtype=np.int32), 64)[0] == -1           # reference index out of range
+    assert join(0, ref_of, 0)[0] == 0

@@ -77,3 +77,20 @@ def test_gpu_chain_recovers_simulated_subclones(gpu_lib, tmp_path):
     mode = int(np.bincount(populated).argmax())
     assert rmse <= 0.06, (rmse, post[::25], truth[::25])
     assert 2 <= mode <= 5, populated
+
+
+def test_library_side_refreshes_equal_the_python_callbacks(gpu_lib, tmp_path, monkeypatch):
+    """The native sweep refreshing the grid itself (pwgs_sweep.ctx: spawned nodes' columns by strided DMA, CNV moves) against
+    the same sweep asking Python to do it through its callbacks: same chain, bit for bit, incl. the LLH trace."""
+    ssm, cnv = os.path.join(cases.GOLDEN, "ssm_data.txt"), os.path.join(cases.GOLDEN, "cnv_data.txt")
+    recs = []
+    for callbacks in ("1", "0"):
+        monkeypatch.setenv("PWGS_SWEEP_CALLBACKS", callbacks)
+        tssb, n_ssms, n_cnvs = chain_util.new_chain(ssm, cnv, gpu_backend, seed=5)
+        recs.append(chain_util.run_chain(tssb, n_ssms, n_cnvs, 10, 300, seed=5))
+        tssb.backend.close()
+    assert sum(r["refreshes"] for r in recs[1]) > 10                        # tree edits did happen
+    for it, (a, b) in enumerate(zip(*recs)):
+        assert np.array_equal(a["assign"], b["assign"]), "assignments diverge at iteration %d" % it
+        assert a["refreshes"] == b["refreshes"] and a["acc"] == b["acc"] and a["llh"] == b["llh"]
+        assert np.array_equal(a["phi"], b["phi"])

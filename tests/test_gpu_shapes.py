@@ -109,3 +109,22 @@ def test_chains_in_one_launch_equal_their_own_launches(oracle, gpu_lib, n_chains
     finally:
         for e in engs:
             e.close()
+
+
+def test_pitched_range_lands_in_the_columns_of_a_wider_grid(oracle, gpu_lib):
+    """pwgs_llh_range_pitched: the column-major block of pwgs_llh_range written in place at out[c * pitch + r] (what the native
+    sweep uses for the columns of spawned nodes); bytes around the block stay as they were."""
+    import ctypes as C
+    from phylowgs_b200 import _lib
+    data, tree = cases.synthetic_case(oracle, n_ssm=700, n_cnv=12, T=2, K=9, seed=33)
+    with cases.engine_for(gpu_lib, data, tree) as eng:
+        D, row0, cols = data.D, 123, np.array([7, 2, 5], dtype=np.int32)
+        want = eng.llh_range(row0, D - row0, cols, gpu_lib.SEM_PY, col_major=True)
+        grid = np.full((5, D), -7.0)
+        _lib.check(_lib.load().pwgs_llh_range_pitched(eng._h, row0, D - row0, len(cols), _lib.p_i32(cols), gpu_lib.SEM_PY | _lib.LAYOUT_COLS,
+                                                     grid[1:, row0:].ctypes.data_as(C.POINTER(C.c_double)), D))
+        assert np.array_equal(grid[1:4, row0:], want)
+        assert (grid[0] == -7.0).all() and (grid[4] == -7.0).all() and (grid[1:4, :row0] == -7.0).all()
+        rc = _lib.load().pwgs_llh_range_pitched(eng._h, row0, D - row0, len(cols), _lib.p_i32(cols), gpu_lib.SEM_PY,
+                                                grid[1:, row0:].ctypes.data_as(C.POINTER(C.c_double)), D)
+        assert rc == -1                                                     # row-major output cannot be pitched
