@@ -103,7 +103,8 @@ class _Grid(object):
         self.calls = 1
         # [K + spare][D]: the columns are views, no copies; the spare rows take the columns of nodes spawned during the sweep
         # (fresh 400 KB arrays per spawned node cost more in page faults than the device call that fills them)
-        self._full = b.grid_t(t.num_data, spare=max(64, K // 2))
+        spare = os.environ.get("PWGS_GRID_SPARE")           # testing: 0 sends every spawned node's column to memory outside the buffer
+        self._full = b.grid_t(t.num_data, spare=int(spare) if spare is not None else max(64, K // 2))
         self.cols = [self._full[k] for k in range(K)]
         if not hasattr(t, "_ssms_of_cnv"):                  # CNV datum index -> SSM datum indices linked to it
             m = {}

@@ -84,13 +84,40 @@ def test_library_side_refreshes_equal_the_python_callbacks(gpu_lib, tmp_path, mo
     the same sweep asking Python to do it through its callbacks: same chain, bit for bit, incl. the LLH trace."""
     ssm, cnv = os.path.join(cases.GOLDEN, "ssm_data.txt"), os.path.join(cases.GOLDEN, "cnv_data.txt")
     recs = []
-    for callbacks in ("1", "0"):
+    for callbacks, spare in (("1", None), ("0", None), ("0", "0")):         # spare 0: spawned nodes' columns outside the grid buffer
         monkeypatch.setenv("PWGS_SWEEP_CALLBACKS", callbacks)
+        if spare is not None:
+            monkeypatch.setenv("PWGS_GRID_SPARE", spare)
         tssb, n_ssms, n_cnvs = chain_util.new_chain(ssm, cnv, gpu_backend, seed=5)
         recs.append(chain_util.run_chain(tssb, n_ssms, n_cnvs, 10, 300, seed=5))
         tssb.backend.close()
     assert sum(r["refreshes"] for r in recs[1]) > 10                        # tree edits did happen
-    for it, (a, b) in enumerate(zip(*recs)):
+    for it, (a, b) in enumerate(zip(recs[1], recs[2])):
+        assert np.array_equal(a["assign"], b["assign"]) and a["llh"] == b["llh"] and a["refreshes"] == b["refreshes"]
+    for it, (a, b) in enumerate(zip(recs[0], recs[1])):
         assert np.array_equal(a["assign"], b["assign"]), "assignments diverge at iteration %d" % it
         assert a["refreshes"] == b["refreshes"] and a["acc"] == b["acc"] and a["llh"] == b["llh"]
         assert np.array_equal(a["phi"], b["phi"])
+
+
+def test_one_tree_sample_at_the_config3_shape(gpu_lib, oracle, tmp_path):
+    """BASELINE.json configs[2] (50k SSMs, 300 CNVs) through one whole tree sample from the one-node start: a sweep that spawns a
+    hundred nodes and moves dozens of CNVs (every refresh done by the library against the device), 60 MH iterations, the LLH
+    trace -- the assignment of every one of the 50 300 data must be the oracle chain's."""
+    from phylowgs_b200 import synth
+    s = synth.config(3)
+    data = oracle.Data(**synth.data_kwargs(s))
+    ssm, cnv = str(tmp_path / "ssm.txt"), str(tmp_path / "cnv.txt")
+    oracle.write_ssm_cnv(data, ssm, cnv)
+    recs = []
+    for factory in (OracleBackend, gpu_backend):
+        tssb, n_ssms, n_cnvs = chain_util.new_chain(ssm, cnv, factory, seed=3)
+        assert (n_ssms, n_cnvs) == (50000, 300)
+        recs.append(chain_util.run_chain(tssb, n_ssms, n_cnvs, 1, 60, seed=3))
+        tssb.backend.close()
+    o, g = recs[0][0], recs[1][0]
+    assert o["refreshes"] == g["refreshes"] and o["refreshes"] > 50
+    assert np.array_equal(o["assign"], g["assign"]) and o["n_nodes"] == g["n_nodes"] and o["n_nodes"] > 50
+    assert o["acc"] == g["acc"]
+    assert np.max(np.abs(o["phi"] - g["phi"])) < 1e-9
+    assert abs(o["llh"] - g["llh"]) <= 1e-9 * abs(o["llh"])
