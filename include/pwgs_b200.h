@@ -142,7 +142,9 @@ int pwgs_get_data_states(pwgs_ctx *ctx, int32_t *M, int32_t *ssm_of_m, int32_t *
  * adapts the actual batch to the running acceptance rate), "mh_ctas" (CTAs per chain, 0 = all SMs) and "mh_collapse" (1: plain
  * data enter the MH likelihood through exact integer totals per (node, error-rate class, sample) instead of one term per datum;
  * off by default, available when the data have at most 16 distinct (mu_r, mu_v) pairs), "mh_big" (-1 = automatic: trees whose
- * node tables (about 18 K T doubles) do not fit in shared memory keep them in global memory; 1 / 0 force / forbid that).  "mh_w_plain", "mh_w_cnv1", "mh_w_cnv2",
+ * node tables (about 18 K T doubles) do not fit in shared memory keep them in global memory; 1 / 0 force / forbid that), "grid_plain"
+ * (1: pwgs_llh_range's column-major form walks the data in file order instead of plain data and CNV-affected SSMs in separate warps;
+ * for A/B timing, the results are the same bits).  "mh_w_plain", "mh_w_cnv1", "mh_w_cnv2",
  * "mh_w_cnv3": relative cost of a warp round (32 data) of plain data / of CNV-affected SSMs with 1, 2, 3 merged states, used to
  * deal whole rounds to the chain's CTAs (defaults 100 / 183 / 429 / 675, fitted to measured per-CTA cycles).  Diagnostics with
  * "mh_profile" = 1: "mh_prof_0".."mh_prof_7" (CTA 0's cycles per phase), "mh_lik_min/max/sum" and "mh_lik_cta_<r>" (likelihood

@@ -71,7 +71,8 @@ struct pwgs_ctx {
     bool grid_timed = false;
     // ---- data set
     int n_ssm = 0, n_cnv = 0, T = 0, D = 0, Dp = 0, M = 0, L = 0;
-    std::vector<int> ssm_of_m;
+    std::vector<int> ssm_of_m, pidx_host;                 // CNV-affected SSMs / plain data, ascending (the two work lists)
+    int opt_grid_plain = 0;                               // 1: the grid kernel walks the data in file order (diagnostic: "grid_plain")
     DevBuf<int> a, d, cnv_ptr, cnv_idx, cnv_c1, cnv_c2;
     DevBuf<double> mu_r, mu_v, lbc;
     DevBuf<int> pidx, pa, pd, pnode, cidx, ca, cd;        // permuted work lists (plain first / CNV-affected SSMs)
@@ -341,6 +342,7 @@ int pwgs_create(int device, int n_ssm, int n_cnv, int ntps,
             CREATE_TRY(cudaStreamSynchronize(s));
         }
     }
+    c->pidx_host = pidx;
     CREATE_TRY(c->pidx.upload(pidx.data(), Dp, s));
     CREATE_TRY(c->pa.upload(pa.data(), (size_t)Dp * T, s));
     CREATE_TRY(c->pd.upload(pd.data(), (size_t)Dp * T, s));
@@ -866,6 +868,18 @@ static int llh_block_impl(pwgs_ctx *c, int row0, int n_rows, const int32_t *rows
     }
     CUDA_TRY(c->scratch.alloc(total));
     CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
+    if (!rows && col_major && n_cols <= 65535 && !c->opt_grid_plain) {
+        // a range of data, column-major (the sweep's calls): plain data and CNV-affected SSMs of the range in separate warps
+        const std::vector<int> &pl = c->pidx_host, &cv = c->ssm_of_m;
+        const int p0 = (int)(std::lower_bound(pl.begin(), pl.end(), row0) - pl.begin());
+        const int p1 = (int)(std::lower_bound(pl.begin(), pl.end(), row0 + n_rows) - pl.begin());
+        const int c0 = (int)(std::lower_bound(cv.begin(), cv.end(), row0) - cv.begin());
+        const int c1 = (int)(std::lower_bound(cv.begin(), cv.end(), row0 + n_rows) - cv.begin());
+        const int np = p1 - p0, nc = c1 - c0, np_pad = (np + 31) & ~31;
+        dim3 grid((unsigned)((np_pad + nc + 127) / 128), (unsigned)n_cols);
+        pair_llh_sorted_kernel<<<grid, 128, 0, c->stream>>>(data_view(c), tree_view(c), row0, n_rows, np, np_pad, c->pidx.p + p0, nc, c->cidx.p + c0,
+                                                            cols ? c->rows.p + nr : nullptr, semantics, kLogTinyMh, kLogTinyPy, kLogQuarter, c->scratch.p);
+    } else
     pair_llh_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(data_view(c), tree_view(c), 0, row0, n_rows, rows ? c->rows.p : nullptr, n_cols,
                                                                             cols ? c->rows.p + nr : nullptr, col_major, semantics, kLogTinyMh, kLogTinyPy,
                                                                             kLogQuarter, c->scratch.p);
@@ -982,6 +996,8 @@ int pwgs_set_option(pwgs_ctx *c, const char *name, int64_t value)
     } else if (n == "mh_big") {
         if (value < -1 || value > 1) return fail(PWGS_EINVAL, "mh_big must be -1 (auto), 0 or 1");
         c->opt_big = (int)value;
+    } else if (n == "grid_plain") {
+        c->opt_grid_plain = value != 0;
     } else if (n == "mh_collapse") {
         c->opt_collapse = value != 0;
     } else if (n == "mh_stage") {

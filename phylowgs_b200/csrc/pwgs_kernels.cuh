@@ -352,6 +352,25 @@ __global__ void pair_llh_kernel(DataView dv, TreeView tv, int mode, int row0, in
     out[i] = datum_ll_at(dv, tv, j, s, semantics, log_tiny_mh, log_tiny_py, log_quarter);
 }
 
+// The grid in the form an assignment sweep asks for -- a range of data x all nodes (or a list of them), column-major -- with
+// warp-uniform work: one block row per node, and within it the plain data of the range first, then (from the next multiple of
+// 32) its CNV-affected SSMs, whose path through datum_ll_at is ~6 times longer.  With the data in file order, where 30 % of the
+// SSMs of a WGS tumour sit in CNVs at random positions, every warp of pair_llh_kernel waited for a handful of such lanes (ncu:
+// 10.9 of 32 threads active per instruction).  Same function per pair, so the same bits.  plain / cnvs: ascending datum indices
+// of the two kinds (fixed for the chain), already offset to the first one inside the range.
+__global__ void pair_llh_sorted_kernel(DataView dv, TreeView tv, int row0, int n_rows, int np, int np_pad, const int *__restrict__ plain,
+                                       int nc, const int *__restrict__ cnvs, const int *__restrict__ cols, int semantics, double log_tiny_mh,
+                                       double log_tiny_py, double log_quarter, double *__restrict__ out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int j;
+    if (r < np) j = plain[r];
+    else if (r >= np_pad && r - np_pad < nc) j = cnvs[r - np_pad];
+    else return;
+    const int s = cols ? cols[blockIdx.y] : (int)blockIdx.y;
+    out[(size_t)blockIdx.y * n_rows + (j - row0)] = datum_ll_at(dv, tv, j, s, semantics, log_tiny_mh, log_tiny_py, log_quarter);
+}
+
 // deterministic single-block sum (thread-strided partial sums, fixed-order combine)
 __global__ void sum_kernel(int n, const double *__restrict__ x, double *out)
 {

@@ -22,5 +22,11 @@ for K in (11, 40, 120):
     ts = []
     for _ in range(3):
         t = time.perf_counter(); g = eng.llh_range(0, D, None, 1, col_major=True, out=buf); ts.append(time.perf_counter() - t)
+    sorted_ns = eng.get_option("grid_kernel_ns")
     t = time.perf_counter(); tot = eng.total_llh(1); t2 = time.perf_counter() - t
-    print("K=%3d: set_tree %.2f ms, grid D x K = %d x %d: %.2f ms end to end, kernel %.3f ms (%.1f MB out), total_llh %.2f ms" % (K, 1e3*(t1-t0), D, K, 1e3*min(ts), eng.get_option("grid_kernel_ns") * 1e-6, g.nbytes/1e6, 1e3*t2))
+    eng.set_option("grid_plain", 1)                  # the same grid with the data walked in file order
+    eng.llh_range(0, D, None, 1, col_major=True, out=buf)
+    plain_ns = eng.get_option("grid_kernel_ns")
+    eng.set_option("grid_plain", 0)
+    print("K=%3d: file-order kernel %.3f ms" % (K, plain_ns * 1e-6))
+    print("K=%3d: set_tree %.2f ms, grid D x K = %d x %d: %.2f ms end to end, kernel %.3f ms (%.1f MB out), total_llh %.2f ms" % (K, 1e3*(t1-t0), D, K, 1e3*min(ts), sorted_ns * 1e-6, g.nbytes/1e6, 1e3*t2))

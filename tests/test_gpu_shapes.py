@@ -128,3 +128,23 @@ def test_pitched_range_lands_in_the_columns_of_a_wider_grid(oracle, gpu_lib):
         rc = _lib.load().pwgs_llh_range_pitched(eng._h, row0, D - row0, len(cols), _lib.p_i32(cols), gpu_lib.SEM_PY,
                                                 grid[1:, row0:].ctypes.data_as(C.POINTER(C.c_double)), D)
         assert rc == -1                                                     # row-major output cannot be pitched
+
+
+@pytest.mark.parametrize("sem", [0, 1])
+def test_grid_kernel_with_sorted_rows_gives_the_file_order_bits(oracle, gpu_lib, sem):
+    """pair_llh_sorted_kernel (plain data and CNV-affected SSMs of a range in separate warps) against pair_llh_kernel walking the
+    same range in file order (option grid_plain): the same function per pair, so the same bits, for whole grids, ranges that
+    start inside either kind, node subsets and ranges without any datum of one kind."""
+    data, tree = cases.synthetic_case(oracle, n_ssm=900, n_cnv=25, T=2, K=10, seed=44)
+    with cases.engine_for(gpu_lib, data, tree) as eng:
+        D = data.D
+        for row0, n_rows, cols in [(0, D, None), (1, D - 1, None), (457, D - 457, np.array([3, 9, 0], dtype=np.int32)),
+                                   (900, 25, None), (880, 40, np.array([5], dtype=np.int32)), (13, 1, None), (D - 1, 1, None)]:
+            eng.set_option("grid_plain", 1)
+            want = eng.llh_range(row0, n_rows, cols, sem, col_major=True)
+            eng.set_option("grid_plain", 0)
+            got = eng.llh_range(row0, n_rows, cols, sem, col_major=True)
+            assert np.array_equal(want, got), (row0, n_rows)
+        rows = np.arange(D, dtype=np.int32)
+        assert rel(eng.llh_rows(rows, sem), oracle.llh_rows(data, tree, rows, sem)) < RTOL
+        assert np.array_equal(eng.llh_range(0, D, None, sem, col_major=True).T, eng.llh_rows(rows, sem))
