@@ -486,7 +486,7 @@ struct MhSmem {
     double *red;                                    // [nb][shares per proposal group]: per-share sums of the current batch
     double *llh;                                    // [MAXB]
     unsigned long long *seen;                       // [2][MAXB][2]: p.sums as of the last time this CTA read each parity
-    double *pscratch;                               // [MH_CWARPS+1][2K] per warp: pi1 and phi1 of a proposal drawn for the ring
+    double *pscratch;                               // [MH_CWARPS+1][4K] per warp: pi1 and phi1 of a proposal drawn for the ring, Euler-tour scan
     volatile int *ctl;                              // producer mailbox, see MhCtl
     int *tin, *tout;                                // [K]
 };
@@ -511,7 +511,7 @@ __host__ __device__ __forceinline__ int mh_phi_at(int b, int i, int KT) { return
 __host__ __device__ inline size_t mh_tree_doubles(int K, int T, int maxb)
 {
     size_t KT = (size_t)K * T;
-    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + 2 * (size_t)K * (MH_CWARPS + 1);
+    return 2 * (4 * KT + 2 * T) + 2 * mh_bufstride(K, T, maxb) + 4 * (size_t)K * (MH_CWARPS + 1);
 }
 // the rest: tables of the logarithm / exponential, per-batch sums and totals
 __host__ __device__ inline size_t mh_fixed_doubles(int maxb)
@@ -536,9 +536,13 @@ __device__ __noinline__ double pwgs_lgamma(double x) { return lgamma(x); }
 // for this sample; for tp == 0 also the log of the iteration's acceptance uniform (mh.cpp:95-96).  Lanes own the nodes
 // k = lane, lane+32, ...; every reduction is a fixed-shape shuffle tree, so all CTAs of a chain get bit-identical results.
 // x / ph: pi1 / phi1 of node k at x[k * xs] / ph[k * phs].
+// (Trees of more than 32 nodes take their subtree sums from a prefix scan over the Euler
+// tour instead of one pass over all nodes per node: at the ~110 nodes of a burn-in tree the K^2 loop, over a scratch array that
+// lives in global memory in that mode, was a third of a draw, and the draws pace the chain there.)
 __device__ __noinline__ void mh_propose(const MhParams &p, const MhSmem &S, int e, double *x, double *ph, int xs, int phs, double *hast_out,
                                         double *logr_out, int tp, uint32_t it, int lane)
 {
+    double *esc = S.pscratch + (size_t)(threadIdx.x >> 5) * 4 * p.K + 2 * p.K;   // this warp's scan scratch (third and fourth K of its 4K)
     const int T = p.T, K = p.K;
     const double mstd = p.mh_std;
     const double *cpi = S.pi(e), *clp = S.lp(e);
@@ -567,6 +571,29 @@ __device__ __noinline__ void mh_propose(const MhParams &p, const MhSmem &S, int 
     }
     const double sa1 = warp_sum(sa);
     __syncwarp();
+    const bool wide = K > 32;
+    if (wide) {
+        // E[tin(k)] = pi1_k, E[tout(k)] = 0; after the inclusive scan phi_k = E[tout(k)] - E[tin(k)] + pi1_k.  Fixed-shape shuffle
+        // scan with a carry between the chunks of 32: the same bits in every CTA; |error| ~ 1e-15 absolute (the sums are <= 1)
+#pragma unroll 1
+        for (int k = lane; k < K; k += 32) { esc[S.tin[k]] = x[k * xs]; esc[S.tout[k]] = 0.0; }
+        __syncwarp();
+        double carry = 0.0;
+#pragma unroll 1
+        for (int base = 0; base < 2 * K; base += 32) {
+            const int t = base + lane;
+            double v = t < 2 * K ? esc[t] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double u = __shfl_up_sync(PWGS_FULL_MASK, v, o);
+                if (lane >= o) v += u;
+            }
+            v += carry;
+            if (t < 2 * K) esc[t] = v;
+            carry = __shfl_sync(PWGS_FULL_MASK, v, 31);
+        }
+        __syncwarp();
+    }
     double t1 = 0.0, t2 = 0.0, slg = 0.0, lgs = 0.0;
 #pragma unroll 1
     for (int k = lane; k <= K; k += 32) {                                        // virtual node K: lgamma(sum alpha) rides along
@@ -574,10 +601,13 @@ __device__ __noinline__ void mh_propose(const MhParams &p, const MhSmem &S, int 
         const int kk = real ? k : 0;
         const int lo = S.tin[kk], hi = S.tout[kk];
         double acc = 0.0;
+        if (wide) acc = esc[hi] - esc[lo] + x[kk * xs];
+        else {
 #pragma unroll 1
-        for (int j = 0; j < K; j++) {                                            // phi_k = sum of pi over the subtree of k
-            double v = x[j * xs];
-            if (lo <= S.tin[j] && S.tout[j] <= hi) acc += v;
+            for (int j = 0; j < K; j++) {                                        // phi_k = sum of pi over the subtree of k
+                double v = x[j * xs];
+                if (lo <= S.tin[j] && S.tout[j] <= hi) acc += v;
+            }
         }
         if (real) ph[k * phs] = acc;
         const double pn = real ? x[kk * xs] : 1.0, pv = cpi[kk * T + tp];
@@ -952,7 +982,7 @@ __device__ __forceinline__ void mh_draw_to_slot(const MhParams &p, const MhSmem 
                                                 int scratch, int lane)
 {
     const int T = p.T, K = p.K, KT = K * T;
-    double *x = S.pscratch + (size_t)scratch * 2 * K;
+    double *x = S.pscratch + (size_t)scratch * 4 * K;
     double hast[3] = {0.0, 0.0, 0.0}, logr = 0.0;
     mh_propose(p, S, e, x, x + K, 1, 1, hast, &logr, tp, it, lane);
     __syncwarp();
@@ -1081,7 +1111,7 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
         S.state0 = t; t += 2 * S.statestride;
         S.bufstride = (int)mh_bufstride(K, T, MAXB); S.o_phi = (int)mh_o_phi(KT, MAXB); S.o_hast = (int)mh_o_hast(KT, MAXB); S.o_logr = S.o_hast + 3 * MAXB * T;
         S.buf0 = t; t += 2 * S.bufstride;
-        S.pscratch = t; t += 2 * K * (MH_CWARPS + 1);
+        S.pscratch = t; t += 4 * K * (MH_CWARPS + 1);
         if (!BIG) q = t;
         S.red = q; q += MH_RED_DOUBLES(MAXB); S.llh = q; q += MAXB;
         S.seen = (unsigned long long *)q; q += 4 * MAXB;

@@ -26,6 +26,8 @@ tssb, n_ssms, n_cnvs = chain_util.new_chain(ssm, cnv, lambda c: GpuBackend(c, 0)
 print("load + context: %.2fs  (%d SSMs, %d CNVs, T=%d)" % (time.time() - t0, n_ssms, n_cnvs, len(tssb.data[0].a)))
 mh_std = 100.0
 import pickle
+from phylowgs_b200.host import fastpickle
+E.tune_allocator(); E.freeze_long_lived()
 E.install_pickle_aliases()
 for it in range(iters):
     t = [time.time()]
@@ -39,7 +41,7 @@ for it in range(iters):
     if 0.5 < acc < 0.99: mh_std /= 2
     tssb.resample_sticks(); tssb.resample_stick_orders(); tssb.resample_hypers(); t.append(time.time())
     llh = tssb.complete_data_log_likelihood(); t.append(time.time())
-    blob = pickle.dumps(tssb, protocol=2); t.append(time.time())
+    blob = fastpickle.dumps(tssb); t.append(time.time())
     d = np.diff(t)
     print("it %2d: total %.3fs | assign %.3f (grid refreshes %d) meta %.3f mh %.4f (acc %.3f std %g) sticks/hypers %.3f llh %.4f pickle %.3f (%d KB) | nodes %d llh %.1f"
           % (it, t[-1] - t[0], d[0], tssb.last_grid_refreshes, d[1], d[2], acc, mh_std, d[3], d[4], d[5], len(blob) // 1024, len(nodes), llh), flush=True)
