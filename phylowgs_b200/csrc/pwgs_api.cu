@@ -657,11 +657,11 @@ static int mh_prepare(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint
     int B = c->opt_batch;
     size_t smem = mh_smem_bytes(c->K, c->T, B);
     while (smem > 176 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B); }
-    // Trees whose node tables leave room for at most 32 proposals per batch in shared memory (K*T from ~85) run with the tables
-    // in global memory and full batches instead: measured faster from there on (config 3 data, 5000 iterations: K = 96 6.7 vs
-    // 6.9 ms, K = 128 9.1 vs 14.0 ms; below, shared memory wins: K = 64 4.5 vs 5.0 ms), and no limit short of device memory
-    // (the reference has none either).
-    const bool big = c->opt_big > 0 || (c->opt_big < 0 && ((B < c->opt_batch && B <= 32) || smem > 200 * 1024));
+    // Trees whose node tables leave room for fewer than 128 proposals per batch in shared memory, from K*T = 56, run with the
+    // tables in global memory and full batches instead: measured faster from there on (config 3 data, 5000 iterations, plain
+    // data collapsed: K = 64 3.1 vs 3.5 ms, K = 128 3.6 vs 13.9 ms; below, shared memory wins: K = 48 3.2 vs 3.3 ms), and no limit
+    // short of device memory (the reference has none either).
+    const bool big = c->opt_big > 0 || (c->opt_big < 0 && ((B < c->opt_batch && (B <= 32 || (size_t)c->K * c->T >= 56)) || smem > 200 * 1024));
     size_t gstride = 0;
     if (big) {
         B = c->opt_batch;

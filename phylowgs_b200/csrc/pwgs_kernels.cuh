@@ -1035,6 +1035,27 @@ __device__ __noinline__ void mh_producer(const MhParams &p, const MhSmem &S, int
     }
 }
 
+// dst[0 .. n) = src[0 .. n) by the consumer threads, both 16-byte aligned: 16-byte L2 loads, eight in flight per thread
+__device__ __forceinline__ void mh_copy_wide(double *dst, const double *src, int n, int tid)
+{
+    if (n <= 0) return;
+    const int n2 = n >> 1;
+    const double2 *s2 = (const double2 *)src;
+    double2 *d2 = (double2 *)dst;
+    int i = tid;
+#pragma unroll 1
+    for (; i + 7 * MH_CONSUMERS < n2; i += 8 * MH_CONSUMERS) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = __ldcg(s2 + i + u * MH_CONSUMERS);
+#pragma unroll
+        for (int u = 0; u < 8; u++) d2[i + u * MH_CONSUMERS] = v[u];
+    }
+#pragma unroll 1
+    for (; i < n2; i += MH_CONSUMERS) d2[i] = __ldcg(s2 + i);
+    if ((n & 1) && tid == 0) dst[n - 1] = __ldcg(src + n - 1);
+}
+
 // Start of an epoch (right after an accept) in distributed mode: the first two batches of the new epoch are drawn once per
 // chain as well.  Every (proposal, sample) has one owner warp somewhere in the chain, the draws land in the two epoch slots
 // of the ring, and one extra chain barrier makes them visible; the first batch is then fetched into proposal buffer `buf`.
@@ -1342,8 +1363,15 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
             if (tid + MH_CONSUMERS < 3 * n1_nb * T) dst[S.o_hast + tid + MH_CONSUMERS] = f_h2;
             if (tid + 2 * MH_CONSUMERS < 3 * n1_nb * T) dst[S.o_hast + tid + 2 * MH_CONSUMERS] = f_h3;
             if (tid < n1_nb) dst[S.o_logr + tid] = f_r;
-            for (int i = tid + MH_CONSUMERS; i < n1_nb * KT; i += MH_CONSUMERS) dst[i] = __ldcg(slot + i);
-            for (int i = tid + MH_CONSUMERS; i < n1_phi; i += MH_CONSUMERS) dst[S.o_phi + i] = __ldcg(slot + S.o_phi + i);
+            if constexpr (BIG) {
+                // node tables in global memory = wide trees: 256 proposals x K nodes x (pi, phi) are tens of thousands of doubles
+                // per batch; with one 8-byte L2 load per thread and trip this copy was half of the kernel at 100 nodes
+                mh_copy_wide(dst + MH_CONSUMERS, slot + MH_CONSUMERS, n1_nb * KT - MH_CONSUMERS, tid);
+                mh_copy_wide(dst + S.o_phi + MH_CONSUMERS, slot + S.o_phi + MH_CONSUMERS, n1_phi - MH_CONSUMERS, tid);
+            } else {
+                for (int i = tid + MH_CONSUMERS; i < n1_nb * KT; i += MH_CONSUMERS) dst[i] = __ldcg(slot + i);
+                for (int i = tid + MH_CONSUMERS; i < n1_phi; i += MH_CONSUMERS) dst[S.o_phi + i] = __ldcg(slot + S.o_phi + i);
+            }
             for (int i = tid + 3 * MH_CONSUMERS; i < 3 * n1_nb * T; i += MH_CONSUMERS) dst[S.o_hast + i] = __ldcg(slot + S.o_hast + i);
         }
         consumer_sync();
