@@ -35,9 +35,8 @@ for it in range(iters):
     acc = r["ratio"]
     pc = [eng.get_option("mh_prof_%d" % i) for i in range(8)]
     tot = max(sum(pc[:7]), 1)
-    print("it %d K=%d std=%g acc=%.4f | flatten %.2f set_tree %.2f launch(host: work list, plan) %.2f wait %.2f [kernel %.3f] write-back %.2f ms | big=%d | %s batches=%d"
+    print("it %d K=%d std=%g acc=%.4f | flatten %.2f set_tree %.2f launch(host: work list, plan) %.2f wait %.2f [kernel %.3f] write-back %.2f ms | %s batches=%d"
           % (it, len(nodes), mh_std, acc, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), r["kernel_ms"], 1e3 * (t5 - t4),
-             eng.get_option("mh_big_used") if False else -1,
              " ".join("%s=%.0f%%" % (n, 100.0 * v / tot) for n, v in zip(names, pc[:7])), pc[7]), flush=True)
     if acc < 0.08 and mh_std < 10000: mh_std *= 2
     if 0.5 < acc < 0.99: mh_std /= 2
