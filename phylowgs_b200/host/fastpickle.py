@@ -210,8 +210,10 @@ class TreePickler(object):
         cap = len(self.blob) + n * (5 + len(tail))
         out = bytearray(p0 + cap + len(suffix))
         out[:p0] = prefix
+        window = (C.c_char * len(out)).from_buffer(out)
         w = lib.pwgs_pickle_join(n, self.blob, self.off.ctypes.data, ref_of.ctypes.data_as(C.POINTER(C.c_int32)), len(nodes),
-                                 refs.ctypes.data, tail, len(tail), C.byref((C.c_char * len(out)).from_buffer(out), p0), cap)
+                                 refs.ctypes.data, tail, len(tail), C.byref(window, p0), cap)
+        del window                                       # the export must be gone before the bytearray is cut to size
         if w < 0:
             return None
         out[p0 + w:p0 + w + len(suffix)] = suffix
