@@ -23,7 +23,7 @@ def test_random_shapes_and_options_walk_the_oracle_chain(oracle, gpu_lib):
         n_ssm = int(rng.choice([40, 200, 700, 3000, 9000]))
         n_cnv = int(rng.choice([0, 0, 3, 12, 40])) if n_ssm >= 200 else int(rng.choice([0, 2]))
         T = int(rng.integers(1, 6))
-        K = int(rng.choice([2, 3, 5, 9, 17, 33, 40]))
+        K = int(rng.choice([2, 3, 5, 9, 17, 33, 40, 64, 100]))      # 64, 100: node tables in global memory, Euler-tour scan
         data, tree = cases.synthetic_case(oracle, n_ssm=n_ssm, n_cnv=n_cnv, T=T, K=K, seed=1000 + case)
         iters = int(rng.choice([1, 7, 60, 250]))
         std = float(rng.choice([30.0, 300.0, 3000.0, 30000.0]))
