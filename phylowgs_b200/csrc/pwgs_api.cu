@@ -657,11 +657,12 @@ static int mh_prepare(pwgs_ctx *c, int iters, double mh_std, uint64_t seed, uint
     int B = c->opt_batch;
     size_t smem = mh_smem_bytes(c->K, c->T, B);
     while (smem > 176 * 1024 && B > 1) { B >>= 1; smem = mh_smem_bytes(c->K, c->T, B); }
-    // Trees whose node tables leave room for fewer than 128 proposals per batch in shared memory, from K*T = 56, run with the
-    // tables in global memory and full batches instead: measured faster from there on (config 3 data, 5000 iterations, plain
-    // data collapsed: K = 64 3.1 vs 3.5 ms, K = 128 3.6 vs 13.9 ms; below, shared memory wins: K = 48 3.2 vs 3.3 ms), and no limit
-    // short of device memory (the reference has none either).
-    const bool big = c->opt_big > 0 || (c->opt_big < 0 && ((B < c->opt_batch && (B <= 32 || (size_t)c->K * c->T >= 56)) || smem > 200 * 1024));
+    // Trees of 48 nodes and more whose node tables do not leave room for a full batch in shared memory run with the tables in
+    // global memory and full batches instead: measured faster from there on, by node count rather than by table size (5000
+    // iterations, plain data collapsed; config 3 data, T = 1: K = 48 3.2 (shared) vs 3.3 ms (global), 56 3.0 vs 3.0, 64 3.5 vs 3.1,
+    // 128 13.9 vs 3.6; config 4 data, T = 5: K = 26 4.1 vs 5.4, 34 4.8 vs 5.4, 48 6.9 vs 5.6, 96 12.5 vs 7.4 --
+    // scripts/mh_big_tree.py, mh_big_tree_t5.py), and no limit short of device memory (the reference has none either).
+    const bool big = c->opt_big > 0 || (c->opt_big < 0 && ((B < c->opt_batch && (c->K >= 48 || B <= 4)) || smem > 200 * 1024));
     size_t gstride = 0;
     if (big) {
         B = c->opt_batch;
