@@ -427,6 +427,9 @@ static_assert(PWGS_MAX_BATCH / 32 <= MH_CWARPS, "the publish / read-totals steps
 #define MH_WIDE_AFTER 8                  // this many all-reject batches in a row: an accept wastes the rest of its batch, so the wide
                                          // batch (half as many chain barriers per iteration) only pays at very low acceptance
 #define MH_DIST_MIN_CTAS 8               // chains with fewer CTAs draw every proposal locally in every CTA
+#ifndef MH_MIN_EPOCH_BATCH
+#define MH_MIN_EPOCH_BATCH 8             // smallest first batch of an epoch that needs the chain barrier anyway
+#endif
 #ifndef MH_EPOCH_LOCAL
 #define MH_EPOCH_LOCAL 1                 // epochs whose first two batches fit one round of local draws start without a chain barrier
 #endif
@@ -1405,7 +1408,12 @@ __global__ void __maxnreg__(MH_MAXNREG) mh_kernel(const MhParams *__restrict__ p
         e ^= 1;
         b_it += sel + 1;
         // after an accept at position sel, expect the next one about as far away: batch = pow2 >= sel+1
-        b_nb = pow2_floor(min(min(batch_cap(0, MAXB), max(1, 2 * pow2_floor(sel + 1))), p.iters - b_it));
+        // ... but no fewer than MH_MIN_EPOCH_BATCH unless the epoch is small enough to start without a chain barrier
+        // (mh_epoch_local): a batch of 8 costs a chain what a batch of 2 costs (latency, not arithmetic, at these sizes) and
+        // wastes less of the fixed price of the next accept
+        int nb0 = 2 * pow2_floor(sel + 1);
+        if (!(MH_EPOCH_LOCAL && dist && 3 * nb0 * T <= MH_CWARPS)) nb0 = max(MH_MIN_EPOCH_BATCH, nb0);
+        b_nb = pow2_floor(min(min(batch_cap(0, MAXB), nb0), p.iters - b_it));
         j = 0;
         mh_adopt_state(S, e, cur, sel, tid);
         consumer_sync();
